@@ -1,0 +1,196 @@
+"""CPU tests that pin the oracle (no GPU).
+
+Golden data come from the reference source itself (tests/golden/make_golden.py):
+the reference's loop operators T_ssy_loops / T_gcy_loops, its model defaults and
+its one recorded Newton trace.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+
+def _load(golden_dir, tag):
+    z = np.load(os.path.join(golden_dir, f"{tag}.npz"))
+    n = len([k for k in z.files if k.startswith("arr")])
+    arrays = tuple(z[f"arr{i}"] for i in range(n))
+    return z, tuple(int(s) for s in z["shapes"]), tuple(z["params"]), arrays
+
+
+@pytest.fixture(scope="module")
+def facts(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "reference_facts.json")))
+
+
+def test_model_defaults_match_reference(facts):
+    s, g = O.SSY(), O.GCY()
+    assert list(s.params) == facts["ssy_params"]
+    assert s.θ == facts["ssy_theta"]
+    assert list(g.params) == facts["gcy_params"]
+    alt = O.SSY(**facts["ssy_alt_kwargs"])
+    assert list(alt.params) == facts["ssy_alt_params"]
+    assert alt.θ == facts["ssy_alt_theta"]
+
+
+def test_rouwenhorst_properties():
+    for n, rho, sig, mu in ((2, 0.9, 0.1, 0.0), (5, 0.987, 0.003, 0.0),
+                            (18, 0.959, 0.0004, 0.0), (7, 0.983, 0.002, -1e-5)):
+        x, P = O.rouwenhorst(n, rho, sig, mu)
+        assert P.shape == (n, n) and np.all(P >= 0)
+        np.testing.assert_allclose(P.sum(1), 1.0, rtol=0, atol=1e-14)
+        # stationary moments of the chain equal those of the AR(1)
+        vals, vecs = np.linalg.eig(P.T)
+        pi = np.real(vecs[:, np.argmax(np.real(vals))])
+        pi /= pi.sum()
+        mean = pi @ x
+        var = pi @ (x - mean) ** 2
+        np.testing.assert_allclose(mean, mu / (1 - rho), rtol=1e-9, atol=1e-15)
+        np.testing.assert_allclose(var, sig ** 2 / (1 - rho ** 2), rtol=1e-9)
+        # conditional mean is exactly AR(1): E[x'|x] = mu + rho x
+        np.testing.assert_allclose(P @ x, mu + rho * x, rtol=1e-10, atol=1e-16)
+
+
+@pytest.mark.parametrize("tag", ["ssy_2345", "ssy_4765"])
+def test_ssy_operator_matches_reference_loops(golden_dir, tag):
+    z, shapes, params, arrays = _load(golden_dir, tag)
+    # the oracle's discretiser still produces the stored factor arrays
+    again = O.discretize_ssy(O.SSY(), shapes)
+    for a, b in zip(arrays, again):
+        np.testing.assert_array_equal(a, b)
+    for w, ref in ((z["w"], z["Tw_ref"]),
+                   (np.full(shapes, 800.0), z["Tw800_ref"])):
+        got = O.T_ssy(w, shapes, params, arrays)
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=0)
+        P, ar, ac, β, θ = O.dense_ssy(shapes, params, arrays)
+        got = O.dense_T(w.reshape(-1), P, ar, ac, β, θ).reshape(shapes)
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=0)
+    if tag == "ssy_2345":
+        got = O.T_ssy_loops(z["w"], shapes, params, arrays)
+        np.testing.assert_allclose(got, z["Tw_ref"], rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("tag", ["gcy_232323", "gcy_234567"])
+def test_gcy_operator_matches_reference_loops(golden_dir, tag):
+    z, shapes, params, arrays = _load(golden_dir, tag)
+    again = O.discretize_gcy(O.GCY(), shapes)
+    for a, b in zip(arrays, again):
+        np.testing.assert_array_equal(a, b)
+    got = O.T_gcy(z["w"], shapes, params, arrays)
+    np.testing.assert_allclose(got, z["Tw_ref"], rtol=1e-13, atol=0)
+    if tag == "gcy_232323":
+        got = O.T_gcy_loops(z["w"], shapes, params, arrays)
+        np.testing.assert_allclose(got, z["Tw_ref"], rtol=1e-14, atol=0)
+        P, ar, ac, β, θ = O.dense_gcy(shapes, params, arrays)
+        np.testing.assert_allclose(P.sum(1), 1.0, atol=1e-13)
+        for w, ref in ((z["w"], z["Tw_ref"]),
+                       (np.full(shapes, 800.0), z["Tw800_ref"])):
+            got = O.dense_T(w.reshape(-1), P, ar, ac, β, θ).reshape(shapes)
+            np.testing.assert_allclose(got, ref, rtol=1e-13, atol=0)
+
+
+def test_analytic_jvp_matches_finite_difference():
+    ssy = O.SSY()
+    shapes = (3, 3, 4, 4)
+    arrays = O.discretize_ssy(ssy, shapes)
+    op = O.KronSSY(shapes, ssy.params, arrays)
+    rng = np.random.default_rng(7)
+    w = 700 + 200 * rng.random(shapes)
+    v = rng.standard_normal(shapes)
+    h = 1e-4
+    fd = (op.T(w + h * v) - op.T(w - h * v)) / (2 * h)
+    np.testing.assert_allclose(op.jvp(w, v), fd, rtol=1e-7, atol=1e-9)
+    P, ar, ac, β, θ = O.dense_ssy(shapes, ssy.params, arrays)
+    dj = O.dense_jvp(w.reshape(-1), v.reshape(-1), P, ar, ac, β, θ)
+    np.testing.assert_allclose(dj.reshape(shapes), op.jvp(w, v), rtol=1e-12)
+
+
+def test_sandpit_newton_trace(facts):
+    """The only numeric output recorded in the reference: Newton on SSY
+    (10,10,10,10) from w0 = 800.  The first two steps are exact Newton steps up
+    to the inexact BiCGSTAB solve (rel. gap < 1e-5); later steps inherit that
+    inexactness (3 digits)."""
+    ssy = O.SSY()
+    shapes = tuple(facts["sandpit_shapes"])
+    op = O.KronSSY(shapes, ssy.params, O.discretize_ssy(ssy, shapes))
+    hist, inner = [], []
+    w, k = O.newton_solver(op.T, np.full(shapes, 800.0), jvp=op.jvp,
+                           verbose=False, history=hist, inner=inner)
+    ref = facts["sandpit_newton_errors"]
+    np.testing.assert_allclose(hist[0], ref[0], rtol=1e-5)
+    np.testing.assert_allclose(hist[1], ref[1], rtol=1e-5)
+    np.testing.assert_allclose(hist[2], ref[2], rtol=1e-3)
+    np.testing.assert_allclose(hist[3], ref[3], rtol=5e-3)
+    # reference stopping quirk: last BiCGSTAB returns x0 = 0 after 0 iterations
+    assert hist[-1] == 0.0 and inner[-1] == 0
+    assert 5 <= k <= 8
+    assert np.linalg.norm(op.T(w) - w) <= 1e-4
+
+
+def test_successive_approx_counts_ssy_default_grid():
+    """BASELINE.md anchor: SSY (2,3,4,5) from 800 takes 10 428 / 12 289 steps."""
+    ssy = O.SSY()
+    shapes = (2, 3, 4, 5)
+    op = O.KronSSY(shapes, ssy.params, O.discretize_ssy(ssy, shapes))
+    w7, k7 = O.successive_approx(op.T, np.full(shapes, 800.0), verbose=False)
+    w8, k8 = O.successive_approx(op.T, np.full(shapes, 800.0), tol=1e-8,
+                                 verbose=False)
+    assert (k7, k8) == (10428, 12289)
+    np.testing.assert_allclose([w8.min(), w8.max()],
+                               [741.6103853, 973.5905061], rtol=1e-9)
+
+
+def test_successive_approx_semantics(capsys):
+    f = lambda x: 0.5 * x + 1.0
+    x, k = O.successive_approx(f, np.array([0.0]), tol=1e-3, verbose=True,
+                               print_skip=2)
+    out = capsys.readouterr().out
+    assert "Beginning iteration" in out and "iter = 0, error = 1.0" in out
+    assert f"Iteration converged after {k} iterations" in out
+    assert abs(x[0] - 2.0) < 2e-3
+    # iterate is accepted even on the terminating step; NaN ends the loop
+    x, k = O.successive_approx(lambda x: x * np.nan, np.array([1.0]), verbose=False)
+    assert k == 1 and np.isnan(x[0])
+    x, k = O.successive_approx(f, np.array([0.0]), tol=0.0, max_iter=5, verbose=False)
+    assert k == 5
+    assert "Warning: Hit maximum iteration number 5" in capsys.readouterr().out
+
+
+def test_bicgstab_and_gmres_solve_linear_system():
+    rng = np.random.default_rng(3)
+    n = 60
+    A = np.eye(n) * 3 + 0.3 * rng.standard_normal((n, n))
+    b = rng.standard_normal(n)
+    info = {}
+    x = O.bicgstab_jax(lambda v: A @ v, b, tol=1e-12, info=info)
+    np.testing.assert_allclose(A @ x, b, rtol=0, atol=1e-10)
+    assert info["iters"] > 0
+    x = O.gmres_restarted(lambda v: A @ v, b, tol=1e-12, restart=20)
+    np.testing.assert_allclose(A @ x, b, rtol=0, atol=1e-9)
+    # zero-iteration exit returns x0 = 0 (the Newton stopping quirk)
+    x = O.bicgstab_jax(lambda v: A @ v, 1e-6 * b / np.linalg.norm(b), atol=1e-4,
+                       info=info)
+    assert info["iters"] == 0 and not x.any()
+
+
+def test_gcy_newton_and_sdf_euler_identity():
+    from oracle.sdf import e_sdf_gcy
+    gcy = O.GCY()
+    shapes = (3,) * 6
+    arrays = O.discretize_gcy(gcy, shapes)
+    op = O.KronGCY(shapes, gcy.params, arrays)
+    w, k = O.newton_solver(op.T, np.full(shapes, 800.0), jvp=op.jvp,
+                           bicgstab_atol=1e-11, verbose=False)
+    w, _ = O.successive_approx(op.T, w, tol=1e-11, verbose=False)
+    assert 456.0 < w.min() < 456.5 and 561.5 < w.max() < 562.0
+    P, ar, ac, β, θ = O.dense_gcy(shapes, gcy.params, arrays)
+    q_f, euler = O.sdf_dense(w, P, ar, ac, e_sdf_gcy(shapes, gcy.params, arrays),
+                             β, θ)
+    assert np.max(np.abs(euler)) < 1e-9
+    assert np.all(q_f > 0.9) and np.all(q_f < 1.01)
+    # explicit rows of Mbar integrate to q_f
+    rows = np.array([0, 17, 728])
+    M = O.sdf_rows(w, P, ac, e_sdf_gcy(shapes, gcy.params, arrays), β, θ, rows)
+    np.testing.assert_allclose((P[rows] * M).sum(1), q_f[rows], rtol=1e-12)
