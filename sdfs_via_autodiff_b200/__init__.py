@@ -1,0 +1,18 @@
+"""B200-native solver for the wealth-consumption-ratio operator, its fixed-point
+loops and the SDF (hot path of jstac/sdfs_via_autodiff code/solvers.py with the
+SSY and GCY discretised models).
+
+Python host + ctypes/DLPack over libsdfs_b200.so (hand-written CUDA for sm_100a).
+Importing this package loads the shared library; if it is missing the import fails
+-- there is no CPU fallback and no PyTorch/Triton path.
+"""
+from ._lib import lib, SdfsError, LIB_PATH                      # noqa: F401
+from .device import Context, DeviceArray, from_dlpack           # noqa: F401
+from .ssy_model import SSY                                       # noqa: F401
+from .gcy_model import GCY                                       # noqa: F401
+from .operator import WCOperator, Factors                        # noqa: F401
+from .ssy_wc_ratio import discretize_ssy, T_ssy, make_T_ssy, test_compute_wc_ratio_ssy   # noqa: F401
+from .gcy_wc_ratio import discretize_gcy, T_gcy, make_T_gcy, test_compute_wc_ratio_gcy   # noqa: F401
+from .solvers import (successive_approx, newton_solver, solver, solvers,                 # noqa: F401
+                      default_tolerance, default_max_iter)
+from .sdf import solve_ssy, solve_gcy, SDFResult                 # noqa: F401

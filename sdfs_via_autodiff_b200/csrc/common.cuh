@@ -1,0 +1,177 @@
+// Shared host/device definitions for libsdfs_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include "../../include/sdfs_b200.h"
+
+namespace cg = cooperative_groups;
+
+#define SDFS_MAX_RANKS 8
+#define SDFS_THREADS 256               // threads per CTA of every streaming kernel
+#define SDFS_WARPS (SDFS_THREADS / 32)
+#define SDFS_MAX_GRID 1024             // upper bound on cooperative grid size (slots)
+
+struct sdfs_comm_state;                // comm.cu
+
+// Peer-visible exchange arena (one per rank, mapped by all peers through CUDA IPC).
+// Layout: [flags | partial slots | xin ping | xin pong]
+struct ArenaView {
+    unsigned long long *flags;         // SDFS_MAX_RANKS monotonically increasing arrival counters
+    double *slots;                     // [SDFS_MAX_RANKS][NSLOT_SETS][SDFS_MAX_GRID] partial reductions
+    double *xin[2];                    // matvec input vectors (full length, padded)
+};
+
+struct sdfs_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int coop_supported = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    // multi-GPU
+    int rank = 0, nranks = 1;
+    sdfs_comm_state *comm = nullptr;
+    // scratch for host-visible results of device loops
+    void *d_status = nullptr;          // LoopStatus
+    void *h_status = nullptr;          // pinned mirror
+};
+
+extern thread_local std::string g_last_error;
+
+int sdfs_set_error(sdfs_ctx *ctx, int code, const char *fmt, ...);
+
+#define CUDA_TRY(ctx, expr)                                                             \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess)                                                          \
+            return sdfs_set_error((ctx), _e == cudaErrorMemoryAllocation ? SDFS_ERR_NOMEM \
+                                                                         : SDFS_ERR_CUDA, \
+                                  "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,         \
+                                  cudaGetErrorString(_e));                              \
+    } while (0)
+
+#define ARG_CHECK(ctx, cond)                                                            \
+    do {                                                                                \
+        if (!(cond))                                                                    \
+            return sdfs_set_error((ctx), SDFS_ERR_ARG, "%s:%d: argument check failed: %s", \
+                                  __FILE__, __LINE__, #cond);                           \
+    } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------
+// Operator description passed by value to kernels.
+// ---------------------------------------------------------------------------
+struct DenseView {
+    const double *P;       // rows [row_begin,row_end), leading dimension ld
+    int64_t N, ld;
+    int64_t row_begin, row_end;
+    const double *a_row;   // N
+    const double *a_col;   // N
+    const double *e_sdf;   // N or null
+    double beta, theta;
+    int vec2;              // 1 when every row of P is 16-byte aligned
+};
+
+// Factor-structured operator: out = M_D ... M_1 applied mode by mode.
+#define SDFS_MAX_DIMS 6
+struct KronMode {
+    const double *mat;     // [n_mats][n][n] row = current index, col = next index
+    int dim;               // tensor axis contracted by this mode
+    int mstride[SDFS_MAX_DIMS];  // matrix id = sum_d coord_d * mstride[d]
+};
+struct KronView {
+    int D;
+    int shape[SDFS_MAX_DIMS];
+    int64_t N;
+    int n_modes;
+    KronMode modes[SDFS_MAX_DIMS];
+    const double *a_row, *a_col, *e_sdf;
+    double beta, theta;
+};
+
+struct sdfs_factors {
+    sdfs_ctx *ctx = nullptr;
+    int model = 0;
+    int D = 0;
+    int shapes[SDFS_MAX_DIMS] = {0};
+    double params[18] = {0};
+    int n_arrays = 0;
+    double *d_arr[16] = {nullptr};
+    int64_t n_elems[16] = {0};
+};
+
+struct sdfs_op {
+    sdfs_ctx *ctx = nullptr;
+    int storage = SDFS_STORAGE_DENSE;
+    DenseView dv{};
+    KronView kv{};
+    sdfs_factors *factors = nullptr;   // borrowed (kept alive by the host wrapper)
+    // owned device memory
+    double *own_P = nullptr, *own_a_row = nullptr, *own_a_col = nullptr, *own_e_sdf = nullptr;
+    // work vectors (each ldv doubles, zero padded), allocated on first use
+    int64_t ldv = 0;
+    double *work = nullptr;            // NWORK * ldv
+    int n_work = 0;
+    double *slots = nullptr;           // reduction slots (single-GPU arena)
+    double *kron_tmp[2] = {nullptr, nullptr};
+    double gamma = 0, psi = 0, mu_c = 0;  // remembered for set_preferences
+};
+
+int op_ensure_work(sdfs_op *op, int n_vectors);
+
+// ---------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// NaN-propagating max (jnp.max semantics, solvers.py:36)
+__device__ __forceinline__ double nanmax(double a, double b) {
+    return (a != a) ? a : ((b != b) ? b : fmax(a, b));
+}
+__device__ __forceinline__ double warp_nanmax(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Streaming 16-byte load of two P entries: read once, evict first, keep L1 for x.
+__device__ __forceinline__ double2 ld_stream2(const double *p) {
+    double2 r;
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ld_stream1(const double *p) {
+    double r;
+    asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+
+// Coherent (weak, L1-cacheable) loads of the matvec input x.  x is rewritten between
+// grid barriers inside the persistent loop kernels, so it must never be turned
+// into a non-coherent ld.global.nc by the compiler.
+__device__ __forceinline__ double2 ld_x2(const double *p) {
+    double2 r;
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ double ld_x1(const double *p) {
+    double r;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(r) : "l"(p) : "memory");
+    return r;
+}
+
+#endif  // __CUDACC__

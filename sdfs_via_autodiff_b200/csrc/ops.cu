@@ -1,0 +1,385 @@
+// Operator handles and single applications: T, JVP, SDF, plain P x.
+#include "common.cuh"
+#include "rowdot.cuh"
+
+int factors_to_kron(const sdfs_factors *f, KronView *kv);
+int launch_build_scalings(sdfs_ctx *ctx, const sdfs_factors *f, const KronView &kv, double gamma,
+                          double theta, double mu_c, double *a_row, double *a_col, double *e_sdf);
+int launch_expand_dense(sdfs_ctx *ctx, const KronView &kv, int64_t row_begin, int64_t row_end, int64_t ld, double *P);
+int comm_allgather_rows(sdfs_ctx *ctx, double *d_vec, int64_t N);   // comm.cu
+
+#define TRY(x) do { int _rc = (x); if (_rc != SDFS_OK) return _rc; } while (0)
+
+// ---------------------------------------------------------------------------
+// Elementwise prologues (N work items; negligible next to the 8 N^2-byte stream)
+// ---------------------------------------------------------------------------
+// mode 0: x = a_col * w^theta                      (T prologue, ssy_wc_ratio.py:145)
+// mode 1: x0 = a_col * w^theta, x1 = a_col * w^(theta-1) * v   (fused T + JVP)
+// mode 2: x0 = a_col * w^theta, x1 = a_col * w^(theta-1)       (SDF)
+// mode 3: x = v                                     (plain P x; stages into the aligned buffer)
+__global__ void k_prologue(int mode, int64_t N, const double *__restrict__ a_col, const double *__restrict__ w,
+                           const double *__restrict__ v, double theta, double *__restrict__ x0,
+                           double *__restrict__ x1) {
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        if (mode == 3) { x0[n] = v[n]; continue; }
+        const double wn = w[n];
+        const double wt = pow(wn, theta);
+        const double ac = a_col[n];
+        x0[n] = ac * wt;
+        if (mode == 1) x1[n] = ac * pow(wn, theta - 1.0) * v[n];
+        else if (mode == 2) x1[n] = ac * pow(wn, theta - 1.0);
+    }
+}
+
+// Epilogue modes of the dense / factor-form pass
+//  0: out0 = 1 + beta (a_row s0)^(1/theta)                                   (T)
+//  1: out0 = beta (a_row s0)^((1-theta)/theta) a_row s1                      (J_T(w) v)
+//  2: out0 = beta^theta e_sdf (w-1)^(1-theta) s1 ; out1 = beta^theta a_row s0/(w-1)^theta - 1 (SDF)
+//  3: out0 = s0                                                              (P x)
+struct EpiArgs {
+    int mode;
+    const double *a_row, *e_sdf, *w;
+    double beta, theta;
+    double *out0, *out1;
+};
+
+__device__ __forceinline__ void apply_epilogue(const EpiArgs &e, int64_t n, double s0, double s1) {
+    if (e.mode == 0) {
+        e.out0[n] = 1.0 + e.beta * pow(e.a_row[n] * s0, 1.0 / e.theta);
+    } else if (e.mode == 1) {
+        const double ar = e.a_row[n];
+        e.out0[n] = e.beta * pow(ar * s0, (1.0 - e.theta) / e.theta) * ar * s1;
+    } else if (e.mode == 2) {
+        const double bt = pow(e.beta, e.theta);
+        const double wm1 = e.w[n] - 1.0;
+        if (e.out0) e.out0[n] = bt * e.e_sdf[n] * pow(wm1, 1.0 - e.theta) * s1;
+        if (e.out1) e.out1[n] = bt * (e.a_row[n] * s0) / pow(wm1, e.theta) - 1.0;
+    } else {
+        e.out0[n] = s0;
+    }
+}
+
+template <int NX>
+__global__ void __launch_bounds__(SDFS_THREADS, 2)
+k_dense_apply(DenseView dv, const double *__restrict__ x0, const double *__restrict__ x1, EpiArgs e) {
+    const int wg = blockIdx.x * SDFS_WARPS + (threadIdx.x >> 5);
+    const int nw = gridDim.x * SDFS_WARPS;
+    dense_rows_pass<NX>(dv, x0, x1, wg, nw,
+                        [&](int64_t n, double s0, double s1) { apply_epilogue(e, n, s0, s1); });
+}
+
+__global__ void k_kron_mode(KronView kv, int m, const double *__restrict__ in, double *__restrict__ out) {
+    kron_mode_pass(kv, m, in, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x,
+                   [&](int64_t idx, double s) { out[idx] = s; });
+}
+// last mode of a two-vector apply: tmpA holds the finished s0 (or unused), the
+// contraction of `in` gives s1 (NX = 2) or s0 (NX = 1)
+__global__ void k_kron_last(KronView kv, int m, const double *__restrict__ in, const double *__restrict__ s0_done,
+                            EpiArgs e) {
+    kron_mode_pass(kv, m, in, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x,
+                   [&](int64_t idx, double s) {
+                       if (s0_done) apply_epilogue(e, idx, s0_done[idx], s);
+                       else apply_epilogue(e, idx, s, s);
+                   });
+}
+
+int op_ensure_work(sdfs_op *op, int n_vectors) {
+    sdfs_ctx *ctx = op->ctx;
+    if (op->n_work >= n_vectors) return SDFS_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (op->work) CUDA_TRY(ctx, cudaFree(op->work));
+    op->work = nullptr;
+    const int64_t N = (op->storage == SDFS_STORAGE_DENSE) ? op->dv.N : op->kv.N;
+    op->ldv = round_up(N, 64) + 64;
+    CUDA_TRY(ctx, cudaMalloc(&op->work, (size_t)n_vectors * op->ldv * sizeof(double)));
+    CUDA_TRY(ctx, cudaMemsetAsync(op->work, 0, (size_t)n_vectors * op->ldv * sizeof(double), ctx->stream));
+    op->n_work = n_vectors;
+    return SDFS_OK;
+}
+
+static inline int ew_grid(sdfs_ctx *ctx, int64_t N) {
+    int64_t g = (N + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+static inline int dense_grid(sdfs_ctx *ctx, const DenseView &dv) {
+    const int64_t nloc = dv.row_end - dv.row_begin;
+    int64_t g = (nloc + SDFS_WARPS * 4 - 1) / (SDFS_WARPS * 4);
+    const int64_t cap = (int64_t)ctx->sm_count * 2;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// Shared driver: prologue -> P pass(es) -> epilogue.
+static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_v, EpiArgs e, bool gather0,
+                     bool gather1) {
+    sdfs_ctx *ctx = op->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool dense = op->storage == SDFS_STORAGE_DENSE;
+    const int64_t N = dense ? op->dv.N : op->kv.N;
+    TRY(op_ensure_work(op, 4));
+    double *x0 = op->work, *x1 = op->work + op->ldv;
+    const int nx = (pmode == 1 || pmode == 2) ? 2 : 1;
+    const double *a_col = dense ? op->dv.a_col : op->kv.a_col;
+    const double theta = dense ? op->dv.theta : op->kv.theta;
+    k_prologue<<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(pmode, N, a_col, d_w, d_v, theta, x0, x1);
+    ctx->launches++;
+    if (dense) {
+        if (op->dv.row_end > op->dv.row_begin) {
+            const int grid = dense_grid(ctx, op->dv);
+            if (nx == 1) k_dense_apply<1><<<grid, SDFS_THREADS, 0, ctx->stream>>>(op->dv, x0, x0, e);
+            else k_dense_apply<2><<<grid, SDFS_THREADS, 0, ctx->stream>>>(op->dv, x0, x1, e);
+            ctx->launches++;
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
+        if (ctx->nranks > 1) {
+            if (gather0 && e.out0) TRY(comm_allgather_rows(ctx, e.out0, N));
+            if (gather1 && e.out1) TRY(comm_allgather_rows(ctx, e.out1, N));
+        }
+    } else {
+        const KronView &kv = op->kv;
+        if (!op->kron_tmp[0]) {
+            CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[0], (size_t)N * sizeof(double)));
+            CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)N * sizeof(double)));
+        }
+        const int grid = ew_grid(ctx, N);
+        double *s0_done = nullptr;
+        for (int pass = 0; pass < nx; ++pass) {
+            const double *in = (pass == 0) ? x0 : x1;
+            // pass 0 of a two-vector apply finishes s0 into work[2]; the last pass feeds the epilogue
+            const bool last_vec = (pass == nx - 1);
+            for (int m = 0; m < kv.n_modes; ++m) {
+                const bool last_mode = (m == kv.n_modes - 1);
+                if (last_mode && last_vec) {
+                    k_kron_last<<<grid, 256, 0, ctx->stream>>>(kv, m, in, s0_done, e);
+                } else {
+                    double *out = last_mode ? (op->work + 2 * op->ldv) : op->kron_tmp[m & 1];
+                    k_kron_mode<<<grid, 256, 0, ctx->stream>>>(kv, m, in, out);
+                    in = out;
+                    if (last_mode) s0_done = out;
+                }
+                ctx->launches++;
+            }
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    return SDFS_OK;
+}
+
+extern "C" {
+
+int sdfs_op_from_dense(sdfs_ctx *ctx, const double *d_P, int64_t N, int64_t ld, int64_t row_begin,
+                       int64_t row_end, const double *d_a_row, const double *d_a_col, double beta,
+                       double theta, sdfs_op **out) {
+    ARG_CHECK(ctx, ctx && out && d_P && d_a_row && d_a_col);
+    ARG_CHECK(ctx, N >= 1 && ld >= N && row_begin >= 0 && row_begin <= row_end && row_end <= N);
+    ARG_CHECK(ctx, theta != 0.0);
+    sdfs_op *op = new sdfs_op();
+    op->ctx = ctx;
+    op->storage = SDFS_STORAGE_DENSE;
+    op->dv.P = d_P; op->dv.N = N; op->dv.ld = ld;
+    op->dv.row_begin = row_begin; op->dv.row_end = row_end;
+    op->dv.a_row = d_a_row; op->dv.a_col = d_a_col; op->dv.e_sdf = nullptr;
+    op->dv.beta = beta; op->dv.theta = theta;
+    op->dv.vec2 = ((ld % 2) == 0 && ((uintptr_t)d_P % 16) == 0) ? 1 : 0;
+    *out = op;
+    return SDFS_OK;
+}
+
+int sdfs_op_from_factors(sdfs_ctx *ctx, sdfs_factors *f, int storage, sdfs_op **out) {
+    ARG_CHECK(ctx, ctx && f && out && f->ctx == ctx);
+    ARG_CHECK(ctx, storage == SDFS_STORAGE_DENSE || storage == SDFS_STORAGE_KRON);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    sdfs_op *op = new sdfs_op();
+    op->ctx = ctx;
+    op->storage = storage;
+    op->factors = f;
+    factors_to_kron(f, &op->kv);
+    const int64_t N = op->kv.N;
+    double beta, gamma, psi, mu_c;
+    if (f->model == SDFS_MODEL_SSY) { beta = f->params[0]; gamma = f->params[1]; psi = f->params[2]; mu_c = f->params[3]; }
+    else { beta = f->params[0]; psi = f->params[1]; gamma = f->params[2]; mu_c = f->params[5]; }
+    op->gamma = gamma; op->psi = psi; op->mu_c = mu_c;
+    const double theta = (1.0 - gamma) / (1.0 - 1.0 / psi);
+    int rc = SDFS_OK;
+    cudaError_t e;
+    if ((e = cudaMalloc(&op->own_a_row, N * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&op->own_a_col, N * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&op->own_e_sdf, N * sizeof(double))) != cudaSuccess) {
+        rc = sdfs_set_error(ctx, SDFS_ERR_NOMEM, "operator scalings (N=%lld): %s", (long long)N, cudaGetErrorString(e));
+        sdfs_op_destroy(op);
+        return rc;
+    }
+    rc = launch_build_scalings(ctx, f, op->kv, gamma, theta, mu_c, op->own_a_row, op->own_a_col, op->own_e_sdf);
+    if (rc) { sdfs_op_destroy(op); return rc; }
+    op->kv.a_row = op->own_a_row; op->kv.a_col = op->own_a_col; op->kv.e_sdf = op->own_e_sdf;
+    op->kv.beta = beta; op->kv.theta = theta;
+    if (storage == SDFS_STORAGE_DENSE) {
+        const int64_t ld = round_up(N, 64);
+        const int64_t chunk = (N + ctx->nranks - 1) / ctx->nranks;
+        int64_t rb = chunk * ctx->rank, re = rb + chunk;
+        if (rb > N) rb = N;
+        if (re > N) re = N;
+        const size_t bytes = (size_t)(re - rb > 0 ? re - rb : 1) * ld * sizeof(double);
+        if ((e = cudaMalloc(&op->own_P, bytes)) != cudaSuccess) {
+            rc = sdfs_set_error(ctx, SDFS_ERR_NOMEM,
+                                "dense P needs %.2f GB on this rank (N=%lld, rows %lld..%lld): %s; use "
+                                "SDFS_STORAGE_KRON or more ranks", bytes / 1e9, (long long)N, (long long)rb,
+                                (long long)re, cudaGetErrorString(e));
+            sdfs_op_destroy(op);
+            return rc;
+        }
+        rc = launch_expand_dense(ctx, op->kv, rb, re, ld, op->own_P);
+        if (rc) { sdfs_op_destroy(op); return rc; }
+        op->dv.P = op->own_P; op->dv.N = N; op->dv.ld = ld;
+        op->dv.row_begin = rb; op->dv.row_end = re;
+        op->dv.a_row = op->own_a_row; op->dv.a_col = op->own_a_col; op->dv.e_sdf = op->own_e_sdf;
+        op->dv.beta = beta; op->dv.theta = theta; op->dv.vec2 = 1;
+    }
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        rc = sdfs_set_error(ctx, SDFS_ERR_CUDA, "operator build: %s", cudaGetErrorString(e));
+        sdfs_op_destroy(op);
+        return rc;
+    }
+    *out = op;
+    return SDFS_OK;
+}
+
+int sdfs_op_destroy(sdfs_op *op) {
+    if (!op) return SDFS_OK;
+    sdfs_ctx *ctx = op->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (op->own_P) cudaFree(op->own_P);
+    if (op->own_a_row) cudaFree(op->own_a_row);
+    if (op->own_a_col) cudaFree(op->own_a_col);
+    if (op->own_e_sdf) cudaFree(op->own_e_sdf);
+    if (op->work) cudaFree(op->work);
+    if (op->slots) cudaFree(op->slots);
+    if (op->kron_tmp[0]) cudaFree(op->kron_tmp[0]);
+    if (op->kron_tmp[1]) cudaFree(op->kron_tmp[1]);
+    delete op;
+    return SDFS_OK;
+}
+
+int sdfs_op_info(sdfs_op *op, int64_t *N, int64_t *ld, int64_t *row_begin, int64_t *row_end, double *beta,
+                 double *theta, int *storage) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_info: NULL op");
+    const bool dense = op->storage == SDFS_STORAGE_DENSE;
+    if (N) *N = dense ? op->dv.N : op->kv.N;
+    if (ld) *ld = dense ? op->dv.ld : 0;
+    if (row_begin) *row_begin = dense ? op->dv.row_begin : 0;
+    if (row_end) *row_end = dense ? op->dv.row_end : op->kv.N;
+    if (beta) *beta = dense ? op->dv.beta : op->kv.beta;
+    if (theta) *theta = dense ? op->dv.theta : op->kv.theta;
+    if (storage) *storage = op->storage;
+    return SDFS_OK;
+}
+
+int sdfs_op_arrays(sdfs_op *op, const double **d_P, const double **d_a_row, const double **d_a_col,
+                   const double **d_e_sdf) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_arrays: NULL op");
+    const bool dense = op->storage == SDFS_STORAGE_DENSE;
+    if (d_P) *d_P = dense ? op->dv.P : nullptr;
+    if (d_a_row) *d_a_row = dense ? op->dv.a_row : op->kv.a_row;
+    if (d_a_col) *d_a_col = dense ? op->dv.a_col : op->kv.a_col;
+    if (d_e_sdf) *d_e_sdf = dense ? op->dv.e_sdf : op->kv.e_sdf;
+    return SDFS_OK;
+}
+
+int sdfs_op_set_esdf(sdfs_op *op, const double *d_e_sdf) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_set_esdf: NULL op");
+    op->dv.e_sdf = d_e_sdf;
+    op->kv.e_sdf = d_e_sdf;
+    return SDFS_OK;
+}
+
+int sdfs_op_set_preferences(sdfs_op *op, double gamma, double psi, double beta) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_set_preferences: NULL op");
+    sdfs_ctx *ctx = op->ctx;
+    ARG_CHECK(ctx, op->factors != nullptr && op->own_a_row != nullptr);
+    ARG_CHECK(ctx, psi != 1.0 && gamma != 1.0);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const double theta = (1.0 - gamma) / (1.0 - 1.0 / psi);
+    TRY(launch_build_scalings(ctx, op->factors, op->kv, gamma, theta, op->mu_c, op->own_a_row, op->own_a_col,
+                              op->own_e_sdf));
+    op->gamma = gamma; op->psi = psi;
+    op->kv.beta = beta; op->kv.theta = theta;
+    op->dv.beta = beta; op->dv.theta = theta;
+    return SDFS_OK;
+}
+
+int sdfs_op_apply_T(sdfs_op *op, const double *d_w_in, double *d_w_out) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_apply_T: NULL op");
+    ARG_CHECK(op->ctx, d_w_in && d_w_out);
+    const bool dense = op->storage == SDFS_STORAGE_DENSE;
+    EpiArgs e{0, dense ? op->dv.a_row : op->kv.a_row, nullptr, nullptr, dense ? op->dv.beta : op->kv.beta,
+              dense ? op->dv.theta : op->kv.theta, d_w_out, nullptr};
+    return run_apply(op, 0, d_w_in, nullptr, e, true, false);
+}
+
+int sdfs_op_apply_jvp(sdfs_op *op, const double *d_w, const double *d_v, double *d_out) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_apply_jvp: NULL op");
+    ARG_CHECK(op->ctx, d_w && d_v && d_out);
+    const bool dense = op->storage == SDFS_STORAGE_DENSE;
+    EpiArgs e{1, dense ? op->dv.a_row : op->kv.a_row, nullptr, nullptr, dense ? op->dv.beta : op->kv.beta,
+              dense ? op->dv.theta : op->kv.theta, d_out, nullptr};
+    return run_apply(op, 1, d_w, d_v, e, true, false);
+}
+
+int sdfs_op_apply_P(sdfs_op *op, const double *d_x, double *d_y) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_apply_P: NULL op");
+    ARG_CHECK(op->ctx, d_x && d_y);
+    EpiArgs e{3, nullptr, nullptr, nullptr, 0.0, 1.0, d_y, nullptr};
+    return run_apply(op, 3, nullptr, d_x, e, true, false);
+}
+
+int sdfs_op_sdf(sdfs_op *op, const double *d_w, double *d_qf, double *d_euler) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_sdf: NULL op");
+    const bool dense = op->storage == SDFS_STORAGE_DENSE;
+    const double *es = dense ? op->dv.e_sdf : op->kv.e_sdf;
+    ARG_CHECK(op->ctx, d_w && (d_qf || d_euler));
+    if (d_qf && !es)
+        return sdfs_set_error(op->ctx, SDFS_ERR_ARG, "sdfs_op_sdf: operator has no e_sdf vector (sdfs_op_set_esdf)");
+    EpiArgs e{2, dense ? op->dv.a_row : op->kv.a_row, es, d_w, dense ? op->dv.beta : op->kv.beta,
+              dense ? op->dv.theta : op->kv.theta, d_qf, d_euler};
+    return run_apply(op, 2, d_w, nullptr, e, true, true);
+}
+
+}  // extern "C"
+
+// Explicit rows of the SDF matrix Mbar(n, n')
+__global__ void k_sdf_rows(int64_t N, const double *__restrict__ w, const double *__restrict__ a_col,
+                           const double *__restrict__ e_sdf, double beta, double theta,
+                           const int64_t *__restrict__ rows, double *__restrict__ out) {
+    const int64_t n = rows[blockIdx.y];
+    const double bt = pow(beta, theta) * e_sdf[n];
+    const double den = w[n] - 1.0;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < N; c += (int64_t)gridDim.x * blockDim.x)
+        out[(int64_t)blockIdx.y * N + c] = bt * a_col[c] * pow(w[c] / den, theta - 1.0);
+}
+
+extern "C" int sdfs_op_sdf_rows(sdfs_op *op, const double *d_w, const int64_t *h_rows, int64_t n_rows,
+                                double *d_out) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_sdf_rows: NULL op");
+    sdfs_ctx *ctx = op->ctx;
+    const bool dense = op->storage == SDFS_STORAGE_DENSE;
+    const int64_t N = dense ? op->dv.N : op->kv.N;
+    const double *es = dense ? op->dv.e_sdf : op->kv.e_sdf;
+    ARG_CHECK(ctx, d_w && h_rows && d_out && n_rows >= 1 && n_rows <= 65535 && es);
+    for (int64_t i = 0; i < n_rows; ++i) ARG_CHECK(ctx, h_rows[i] >= 0 && h_rows[i] < N);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int64_t *d_rows = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d_rows, n_rows * sizeof(int64_t)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_rows, h_rows, n_rows * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((unsigned)((N + 255) / 256 < 1024 ? (N + 255) / 256 : 1024), (unsigned)n_rows);
+    k_sdf_rows<<<grid, 256, 0, ctx->stream>>>(N, d_w, dense ? op->dv.a_col : op->kv.a_col, es,
+                                              dense ? op->dv.beta : op->kv.beta,
+                                              dense ? op->dv.theta : op->kv.theta, d_rows, d_out);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaFree(d_rows));
+    return SDFS_OK;
+}

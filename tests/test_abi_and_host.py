@@ -1,0 +1,78 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol, and the
+host-side mirror of the reference interface behaves like the reference (no GPU,
+no compute calls)."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sdfs_via_autodiff_b200 as S
+from sdfs_via_autodiff_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 45
+    for name in declared:
+        assert hasattr(_lib.lib, name), f"{name} declared in include/sdfs_b200.h but not exported"
+    # and every bound signature is declared in the header
+    assert set(_lib._SIGS) <= set(declared)
+    assert _lib.lib.sdfs_abi_version() == 1
+    assert b"sm_100a" in _lib.lib.sdfs_version_string()
+
+
+def test_header_cites_reference_for_each_group():
+    text = open(_lib.HEADER).read()
+    for cite in ("solvers.py:19-48", "solvers.py:51-95", "ssy_wc_ratio.py:23-79",
+                 "gcy_wc_ratio.py:31-131", "temp_ssy.py:204-216", "autosdfs.tex:374-384"):
+        assert cite in text
+
+
+def test_no_cpu_fallback_without_gpu():
+    import ctypes as C
+    h = C.c_void_p()
+    n = C.c_int()
+    rc = _lib.lib.sdfs_ctx_create(10_000, C.byref(h))
+    assert rc != 0 and not h.value
+    assert _lib.lib.sdfs_last_error(None)
+    # product package never imports the oracle
+    pkg = os.path.dirname(S.__file__)
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+            assert "import torch" not in src and "import triton" not in src, fn
+
+
+def test_models_match_reference_defaults(golden_dir):
+    facts = json.load(open(os.path.join(golden_dir, "reference_facts.json")))
+    s, g = S.SSY(), S.GCY()
+    assert [float(x) for x in s.params] == facts["ssy_params"]
+    assert float(s.θ) == facts["ssy_theta"]
+    assert [float(x) for x in g.params] == facts["gcy_params"]
+    assert not hasattr(g, "θ")                      # like the reference
+    alt = S.SSY(**facts["ssy_alt_kwargs"])
+    assert [float(x) for x in alt.params] == facts["ssy_alt_params"]
+
+
+def test_solver_front_end_semantics(capsys):
+    f = lambda x: 0.5 * x + 1.0                     # generic callable: host-driven loop
+    x, k = S.successive_approx(f, np.array([0.0]), tol=1e-3, print_skip=2)
+    out = capsys.readouterr().out
+    assert out.startswith("Beginning iteration\n\n\n")
+    assert "iter = 0, error = 1.0" in out and f"Iteration converged after {k} iterations" in out
+    assert abs(x[0] - 2.0) < 2e-3
+    assert set(S.solvers) == {"newton", "anderson", "gd", "successive_approx"}
+    x = S.solver(f, np.array([0.0]), algorithm="no-such-algo")
+    out = capsys.readouterr().out
+    assert "Algorithm no-such-algo not found." in out and "Falling back to successive approximation." in out
+    assert abs(x[0] - 2.0) < 1e-6
+    x, k = S.successive_approx(f, np.array([0.0]), tol=0.0, max_iter=7, verbose=False)
+    assert k == 7 and "Warning: Hit maximum iteration number 7" in capsys.readouterr().out
+    with pytest.raises(TypeError):
+        S.newton_solver(f, np.array([0.0]), verbose=False)
+    with pytest.raises(NotImplementedError):
+        S.solvers["anderson"](f, np.array([0.0]))
+    assert S.default_tolerance == 1e-7 and S.default_max_iter == 1000000
