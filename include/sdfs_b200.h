@@ -63,6 +63,11 @@ int sdfs_ctx_device(sdfs_ctx *ctx, int *device, int *sm_count, size_t *free_byte
 /* Kernel launches issued by this context since creation (bench.py's
  * "gpu_launches" evidence). */
 int64_t sdfs_ctx_launch_count(sdfs_ctx *ctx);
+/* Per-launch CUDA-event timing of the dominant kernel (the dense row-stream pass) on the
+ * launching stream: enable for up to max_launches launches (0 disables), then read the
+ * summed device time and the number of launches recorded (the read synchronises). */
+int sdfs_prof_enable(sdfs_ctx *ctx, int max_launches);
+int sdfs_prof_read(sdfs_ctx *ctx, double *total_ms, int64_t *launches);
 /* CUDA-event timer on the context's stream. */
 int sdfs_timer_start(sdfs_ctx *ctx);
 int sdfs_timer_stop_ms(sdfs_ctx *ctx, double *ms);

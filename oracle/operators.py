@@ -196,3 +196,26 @@ def dense_jvp(w, v, P, a_row, a_col, β, θ):
     """J_T(w) v from temp_ssy.py:204-216 (without the '- I')."""
     s = a_row * (P @ (a_col * w ** θ))
     return β * s ** ((1 - θ) / θ) * a_row * (P @ (a_col * w ** (θ - 1) * v))
+
+
+# --------------------------------------------------------------------------
+# Reference-faithful broadcast form restricted to a slab of current states.
+# This is the arithmetic the reference actually performs (ssy_wc_ratio.py:116-148:
+# a 2D-axis broadcast product H followed by a sum over the next-period axes), i.e.
+# N^2 multiply-adds per evaluation with no sum-factorisation.  Used as the CPU
+# baseline of bench.py on a bounded sample of (l, k) slabs.
+# --------------------------------------------------------------------------
+def ssy_broadcast_slab(op, w, l, k):
+    """Tw[l, k, :, :] computed the reference's way for one (l, k) pair."""
+    L, K, I, J = op.shapes
+    γ, θ = op.γ, op.θ
+    A1 = np.exp(θ * op.h_λ)[None, None, :, None, None, None]              # jn_h_lam
+    A2 = np.exp(0.5 * ((1 - γ) * op.σ_c[k]) ** 2)                          # n_h_c (scalar here)
+    A3 = np.exp((1 - γ) * (op.μ_c + op.z))[:, :, None, None, None, None]   # n_h_z, n_z
+    Qλ = op.Q_λ[l][None, None, :, None, None, None]
+    Qc = op.Q_c[k][None, None, None, :, None, None]
+    Qhz = op.Q_hz[:, None, None, None, :, None]
+    zQ = op.z_Q[:, :, None, None, None, :]
+    H = A1 * A2 * A3 * Qλ * Qc * Qhz * zQ                                  # (I, J, L, K, I, J)
+    Hwθ = np.sum(w[None, None] ** θ * H, axis=(2, 3, 4, 5))
+    return 1 + op.β * Hwθ ** (1 / θ)

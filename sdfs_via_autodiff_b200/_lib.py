@@ -43,6 +43,8 @@ _SIGS = {
     "sdfs_ctx_device_sync": (C.c_int, [c_vp]),
     "sdfs_ctx_device": (C.c_int, [c_vp, P(C.c_int), P(C.c_int), P(C.c_size_t), P(C.c_size_t)]),
     "sdfs_ctx_launch_count": (c_i64, [c_vp]),
+    "sdfs_prof_enable": (C.c_int, [c_vp, C.c_int]),
+    "sdfs_prof_read": (C.c_int, [c_vp, P(c_f64), P(c_i64)]),
     "sdfs_timer_start": (C.c_int, [c_vp]),
     "sdfs_timer_stop_ms": (C.c_int, [c_vp, P(c_f64)]),
     "sdfs_malloc": (C.c_int, [c_vp, C.c_size_t, P(c_vp)]),

@@ -48,6 +48,12 @@ int sdfs_ctx_create(int device, sdfs_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->coop_supported = prop.cooperativeLaunch;
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        cudaMemPool_t pool;
+        CUDA_TRY(nullptr, cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ull;   // keep freed blocks cached in the pool
+        CUDA_TRY(nullptr, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CUDA_TRY(nullptr, cudaEventCreate(&ctx->ev0));
     CUDA_TRY(nullptr, cudaEventCreate(&ctx->ev1));
     CUDA_TRY(nullptr, cudaMalloc(&ctx->d_status, 4096));
@@ -66,6 +72,7 @@ int sdfs_ctx_destroy(sdfs_ctx *ctx) {
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t ev : ctx->prof_ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SDFS_OK;
@@ -119,12 +126,43 @@ int sdfs_timer_stop_ms(sdfs_ctx *ctx, double *ms) {
     return SDFS_OK;
 }
 
+int sdfs_prof_enable(sdfs_ctx *ctx, int max_launches) {
+    ARG_CHECK(ctx, ctx != nullptr && max_launches >= 0 && max_launches <= (1 << 20));
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    while (ctx->prof_ev.size() < (size_t)max_launches * 2) {
+        cudaEvent_t ev;
+        CUDA_TRY(ctx, cudaEventCreate(&ev));
+        ctx->prof_ev.push_back(ev);
+    }
+    ctx->prof_used = 0;
+    ctx->prof_on = max_launches > 0;
+    return SDFS_OK;
+}
+
+int sdfs_prof_read(sdfs_ctx *ctx, double *total_ms, int64_t *launches) {
+    ARG_CHECK(ctx, ctx != nullptr && total_ms && launches);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = (int64_t)(ctx->prof_used / 2);
+    ctx->prof_used = 0;
+    return SDFS_OK;
+}
+
 int sdfs_malloc(sdfs_ctx *ctx, size_t bytes, void **d_ptr) {
     ARG_CHECK(ctx, ctx != nullptr && d_ptr != nullptr);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     *d_ptr = nullptr;
     if (bytes == 0) bytes = 8;
-    CUDA_TRY(ctx, cudaMalloc(d_ptr, bytes));
+    // stream-ordered pool: no device-wide synchronisation per allocation (cudaMalloc/cudaFree
+    // cost ~100 ms each once an 88 GB operator is mapped)
+    CUDA_TRY(ctx, cudaMallocAsync(d_ptr, bytes, ctx->stream));
     return SDFS_OK;
 }
 
@@ -132,8 +170,7 @@ int sdfs_free(sdfs_ctx *ctx, void *d_ptr) {
     ARG_CHECK(ctx, ctx != nullptr);
     if (!d_ptr) return SDFS_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    CUDA_TRY(ctx, cudaFree(d_ptr));
+    CUDA_TRY(ctx, cudaFreeAsync(d_ptr, ctx->stream));
     return SDFS_OK;
 }
 

@@ -13,7 +13,7 @@
 namespace cg = cooperative_groups;
 
 #define SDFS_MAX_RANKS 8
-#define SDFS_THREADS 256               // threads per CTA of every streaming kernel
+#define SDFS_THREADS 288               // 8 consumer warps + 1 TMA producer warp
 #define SDFS_WARPS (SDFS_THREADS / 32)
 #define SDFS_MAX_GRID 1024             // upper bound on cooperative grid size (slots)
 
@@ -35,6 +35,10 @@ struct sdfs_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     int64_t launches = 0;
+    // optional per-launch CUDA-event timing of the dominant (dense pass) kernel
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop)
+    size_t prof_used = 0;
     // multi-GPU
     int rank = 0, nranks = 1;
     sdfs_comm_state *comm = nullptr;

@@ -201,8 +201,18 @@ __device__ __forceinline__ void store_all_ranks(const LoopEnv &env, int buf, int
 
 // ---- operator abstraction ---------------------------------------------------
 // apply(view, xin, epi): epi(n, s) for every row n owned by this rank, s = (P xin)[n].
+struct Scratch {
+    RowPipe<1> *rp;        // TMA ring in dynamic shared memory (dense operators)
+    PipeState st;
+};
+
 struct DenseLoopOp {
+    static constexpr int kMinBlocks = 1;
     DenseView dv;
+    __host__ __device__ size_t dyn_smem() const { return dv.vec2 ? sizeof(RowPipe<1>) : 0; }
+    __device__ __forceinline__ void init(Scratch &sc) const {
+        if (dv.vec2) pipe_init(sc.rp, sc.st);
+    }
     __device__ __forceinline__ int64_t N() const { return dv.N; }
     __device__ __forceinline__ int64_t row_begin() const { return dv.row_begin; }
     __device__ __forceinline__ int64_t row_end() const { return dv.row_end; }
@@ -211,18 +221,19 @@ struct DenseLoopOp {
     __device__ __forceinline__ double beta() const { return dv.beta; }
     __device__ __forceinline__ double theta() const { return dv.theta; }
     template <class Epi>
-    __device__ __forceinline__ bool apply(cg::grid_group &, const LoopEnv &, unsigned long long &, const double *xin,
-                                          Epi &&epi) const {
-        const int wg = blockIdx.x * SDFS_WARPS + (threadIdx.x >> 5);
-        const int nw = gridDim.x * SDFS_WARPS;
-        dense_rows_pass<1>(dv, xin, xin, wg, nw, [&](int64_t n, double s0, double) { epi(n, s0); });
+    __device__ __forceinline__ bool apply(cg::grid_group &, const LoopEnv &, unsigned long long &, Scratch &sc,
+                                          const double *xin, Epi &&epi) const {
+        dense_pass<1>(dv, xin, xin, sc.rp, sc.st, [&](int64_t n, double s0, double) { epi(n, s0); });
         return true;
     }
 };
 
 struct KronLoopOp {
+    static constexpr int kMinBlocks = 2;
     KronView kv;
     double *tmp0, *tmp1;
+    __host__ __device__ size_t dyn_smem() const { return 0; }
+    __device__ __forceinline__ void init(Scratch &) const {}
     __device__ __forceinline__ int64_t N() const { return kv.N; }
     __device__ __forceinline__ int64_t row_begin() const { return 0; }
     __device__ __forceinline__ int64_t row_end() const { return kv.N; }
@@ -232,7 +243,7 @@ struct KronLoopOp {
     __device__ __forceinline__ double theta() const { return kv.theta; }
     template <class Epi>
     __device__ __forceinline__ bool apply(cg::grid_group &grid, const LoopEnv &env, unsigned long long &epoch,
-                                          const double *xin, Epi &&epi) const {
+                                          Scratch &, const double *xin, Epi &&epi) const {
         const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         const int64_t nth = (int64_t)gridDim.x * blockDim.x;
         const double *in = xin;
@@ -261,9 +272,13 @@ struct SAArgs {
 };
 
 template <class Op>
-__global__ void __launch_bounds__(SDFS_THREADS, 2) k_sa_loop(Op op, SAArgs a, LoopEnv env) {
+__global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_sa_loop(Op op, SAArgs a, LoopEnv env) {
     cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ double smem[SDFS_WARPS * NVAL + NVAL];
+    Scratch sc;
+    sc.rp = reinterpret_cast<RowPipe<1> *>(dyn_smem);
+    op.init(sc);
     unsigned long long epoch = env.epoch0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(SDFS_THREADS, 2) k_sa_loop(Op op, SAArgs a, Lo
         const double *w_cur = a.w[cur];
         double *w_nxt = a.w[nxt];
         double part[1] = {0.0};
-        bool ok = op.apply(grid, env, epoch, env.xin[env.rank][cur], [&](int64_t n, double s) {
+        bool ok = op.apply(grid, env, epoch, sc, env.xin[env.rank][cur], [&](int64_t n, double s) {
             const double y = 1.0 + beta * pow(a_row[n] * s, inv_theta);
             w_nxt[n] = y;
             store_all_ranks(env, nxt, n, a_col[n] * pow(y, theta));
@@ -332,7 +347,7 @@ enum { SET_B = 0, SET_D = 1, SET_E = 2, SET_F = 3, SET_G = 4, SET_H = 5, SET_X =
 
 template <class Op>
 __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &op, const NewtonArgs &a,
-                                                const LoopEnv &env, unsigned long long &epoch, double *smem,
+                                                const LoopEnv &env, unsigned long long &epoch, Scratch &sc, double *smem,
                                                 double bs, long long &k_out, long long &matvecs) {
     // on entry: r = rhat = p = q = g (= b), x = 0; bs = <b,b>
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,7 +370,7 @@ __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &
         if (!all_sync(grid, env, epoch)) return false;
         // D: q = J p = d .* P(c .* p) - p ; <rhat,q>
         double v1[1] = {0.0};
-        if (!op.apply(grid, env, epoch, env.xin[env.rank][0], [&](int64_t n, double sum) {
+        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double sum) {
                 const double qn = a.d[n] * sum - a.p[n];
                 a.q[n] = qn;
                 v1[0] += a.rhat[n] * qn;
@@ -374,7 +389,7 @@ __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &
         const bool exit_early = v2[0] < atol2;
         // F: t = J s ; <t,s>, <t,t>
         double v3[2] = {0.0, 0.0};
-        if (!op.apply(grid, env, epoch, env.xin[env.rank][0], [&](int64_t n, double sum) {
+        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double sum) {
                 const double sn = a.s[n];
                 const double tn = a.d[n] * sum - sn;
                 a.t[n] = tn;
@@ -419,7 +434,7 @@ __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &
 // x0 = 0; stops when |residual estimate| <= max(rtol ||b||, atol).
 template <class Op>
 __device__ __forceinline__ bool gmres_device(cg::grid_group &grid, const Op &op, const NewtonArgs &a,
-                                             const LoopEnv &env, unsigned long long &epoch, double *smem,
+                                             const LoopEnv &env, unsigned long long &epoch, Scratch &sc, double *smem,
                                              double *hs /* shared: Hessenberg workspace */, double bs,
                                              long long &k_out, long long &matvecs) {
     // on entry: r = g (= b), x = 0
@@ -453,7 +468,7 @@ __device__ __forceinline__ bool gmres_device(cg::grid_group &grid, const Op &op,
             double *Vj = a.V + (long long)j * a.ldv;
             double *Wv = a.V + (long long)(j + 1) * a.ldv;
             // w = J V_j
-            if (!op.apply(grid, env, epoch, env.xin[env.rank][0], [&](int64_t n, double sum) {
+            if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double sum) {
                     Wv[n] = a.d[n] * sum - Vj[n];
                 })) return false;
             its += 1;
@@ -548,7 +563,7 @@ __device__ __forceinline__ bool gmres_device(cg::grid_group &grid, const Op &op,
         if (!all_sync(grid, env, epoch)) return false;
         // true residual r = b - J x
         double rv[1] = {0.0};
-        if (!op.apply(grid, env, epoch, env.xin[env.rank][0], [&](int64_t n, double sum) {
+        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double sum) {
                 const double rn = a.g[n] - (a.d[n] * sum - a.x[n]);
                 a.r[n] = rn;
                 rv[0] += rn * rn;
@@ -562,9 +577,13 @@ __device__ __forceinline__ bool gmres_device(cg::grid_group &grid, const Op &op,
 }
 
 template <class Op>
-__global__ void __launch_bounds__(SDFS_THREADS, 2) k_newton_loop(Op op, NewtonArgs a, LoopEnv env) {
+__global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_newton_loop(Op op, NewtonArgs a, LoopEnv env) {
     cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ double smem[SDFS_WARPS * NVAL + NVAL];
+    Scratch sc;
+    sc.rp = reinterpret_cast<RowPipe<1> *>(dyn_smem);
+    op.init(sc);
     __shared__ double hs[(GMRES_MAX_RESTART + 1) * 2 + GMRES_MAX_RESTART * 3 + GMRES_MAX_RESTART * GMRES_MAX_RESTART];
     unsigned long long epoch = env.epoch0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -588,7 +607,7 @@ __global__ void __launch_bounds__(SDFS_THREADS, 2) k_newton_loop(Op op, NewtonAr
     while (error > a.tol && it < a.max_iter) {
         // B: s = a_row P xin ; Tw ; g = Tw - w ; d ; Krylov init ; <g,g>
         double vb[1] = {0.0};
-        if (!op.apply(grid, env, epoch, env.xin[env.rank][0], [&](int64_t n, double sum) {
+        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double sum) {
                 const double ar = a_row[n];
                 const double sv = ar * sum;
                 const double gn = (1.0 + beta * pow(sv, inv_theta)) - a.w[n];
@@ -602,9 +621,9 @@ __global__ void __launch_bounds__(SDFS_THREADS, 2) k_newton_loop(Op op, NewtonAr
         if (!grid_allreduce<1, false>(grid, env, epoch, SET_B, vb, smem)) return;
         long long k_inner = 0;
         if (a.krylov == SDFS_KRYLOV_BICGSTAB) {
-            if (!bicgstab_device(grid, op, a, env, epoch, smem, vb[0], k_inner, matvecs)) return;
+            if (!bicgstab_device(grid, op, a, env, epoch, sc, smem, vb[0], k_inner, matvecs)) return;
         } else {
-            if (!gmres_device(grid, op, a, env, epoch, smem, hs, vb[0], k_inner, matvecs)) return;
+            if (!gmres_device(grid, op, a, env, epoch, sc, smem, hs, vb[0], k_inner, matvecs)) return;
         }
         inner_total += (k_inner > 0 ? k_inner : 0);
         // H: w <- w - x ; error = max|x| ; next xin, c
@@ -670,20 +689,25 @@ static int build_env(sdfs_op *op, LoopEnv *env) {
 }
 
 template <class Kern>
-static int coop_grid(sdfs_ctx *ctx, Kern kern, int64_t work_rows, int *grid_out) {
+static int coop_grid(sdfs_ctx *ctx, Kern kern, size_t dyn_smem, int max_per_sm, int64_t work_groups, int *grid_out) {
+    if (dyn_smem > 0) CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     int per_sm = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SDFS_THREADS, 0));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SDFS_THREADS, dyn_smem));
     if (per_sm < 1) return sdfs_set_error(ctx, SDFS_ERR_CUDA, "cooperative kernel does not fit on an SM");
-    if (per_sm > 2) per_sm = 2;
+    if (per_sm > max_per_sm) per_sm = max_per_sm;
     int64_t grid = (int64_t)per_sm * ctx->sm_count;
     if (ctx->nranks == 1) {   // small problems: fewer CTAs make the grid barrier cheaper
-        int64_t want = (work_rows + SDFS_WARPS * 4 - 1) / (SDFS_WARPS * 4);
-        if (want < 1) want = 1;
+        int64_t want = work_groups < 1 ? 1 : work_groups;
         if (want < grid) grid = want;
     }
     if (grid > SDFS_MAX_GRID) grid = SDFS_MAX_GRID;
     *grid_out = (int)grid;
     return SDFS_OK;
+}
+
+static inline int64_t dense_groups(const DenseView &dv) {
+    const int64_t g = (dv.row_end - dv.row_begin + TR - 1) / TR;
+    return dv.vec2 ? g : (g + SDFS_WARPS - 1) / SDFS_WARPS;
 }
 
 static int finish_loop(sdfs_ctx *ctx, LoopStatus *hs, unsigned long long epochs_hint) {
@@ -724,16 +748,16 @@ int sdfs_solve_sa(sdfs_op *op, const double *d_w_init, double tol, int64_t max_i
     const bool dense = op->storage == SDFS_STORAGE_DENSE;
     if (dense) {
         DenseLoopOp lop{op->dv};
-        TRY(coop_grid(ctx, k_sa_loop<DenseLoopOp>, op->dv.row_end - op->dv.row_begin, &grid));
+        TRY(coop_grid(ctx, k_sa_loop<DenseLoopOp>, lop.dyn_smem(), 1, dense_groups(op->dv), &grid));
         void *args[] = {&lop, &a, &env};
-        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sa_loop<DenseLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, 0, ctx->stream));
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sa_loop<DenseLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, lop.dyn_smem(), ctx->stream));
     } else {
         if (!op->kron_tmp[0]) {
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[0], (size_t)op->kv.N * sizeof(double)));
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)op->kv.N * sizeof(double)));
         }
         KronLoopOp lop{op->kv, op->kron_tmp[0], op->kron_tmp[1]};
-        TRY(coop_grid(ctx, k_sa_loop<KronLoopOp>, op->kv.N / 8, &grid));
+        TRY(coop_grid(ctx, k_sa_loop<KronLoopOp>, 0, 2, (op->kv.N + SDFS_THREADS - 1) / SDFS_THREADS, &grid));
         void *args[] = {&lop, &a, &env};
         CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sa_loop<KronLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, 0, ctx->stream));
     }
@@ -783,16 +807,16 @@ int sdfs_solve_newton(sdfs_op *op, const double *d_w_init, double tol, int64_t m
     int grid = 0;
     if (dense) {
         DenseLoopOp lop{op->dv};
-        TRY(coop_grid(ctx, k_newton_loop<DenseLoopOp>, op->dv.row_end - op->dv.row_begin, &grid));
+        TRY(coop_grid(ctx, k_newton_loop<DenseLoopOp>, lop.dyn_smem(), 1, dense_groups(op->dv), &grid));
         void *args[] = {&lop, &a, &env};
-        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_newton_loop<DenseLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, 0, ctx->stream));
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_newton_loop<DenseLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, lop.dyn_smem(), ctx->stream));
     } else {
         if (!op->kron_tmp[0]) {
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[0], (size_t)N * sizeof(double)));
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)N * sizeof(double)));
         }
         KronLoopOp lop{op->kv, op->kron_tmp[0], op->kron_tmp[1]};
-        TRY(coop_grid(ctx, k_newton_loop<KronLoopOp>, N / 8, &grid));
+        TRY(coop_grid(ctx, k_newton_loop<KronLoopOp>, 0, 2, (N + SDFS_THREADS - 1) / SDFS_THREADS, &grid));
         void *args[] = {&lop, &a, &env};
         CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_newton_loop<KronLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, 0, ctx->stream));
     }

@@ -60,12 +60,13 @@ __device__ __forceinline__ void apply_epilogue(const EpiArgs &e, int64_t n, doub
 }
 
 template <int NX>
-__global__ void __launch_bounds__(SDFS_THREADS, 2)
-k_dense_apply(DenseView dv, const double *__restrict__ x0, const double *__restrict__ x1, EpiArgs e) {
-    const int wg = blockIdx.x * SDFS_WARPS + (threadIdx.x >> 5);
-    const int nw = gridDim.x * SDFS_WARPS;
-    dense_rows_pass<NX>(dv, x0, x1, wg, nw,
-                        [&](int64_t n, double s0, double s1) { apply_epilogue(e, n, s0, s1); });
+__global__ void __launch_bounds__(SDFS_THREADS, 1)
+k_dense_apply(DenseView dv, const double *x0, const double *x1, EpiArgs e) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    RowPipe<NX> *rp = reinterpret_cast<RowPipe<NX> *>(dyn_smem);
+    PipeState st;
+    if (dv.vec2) pipe_init(rp, st);
+    dense_pass<NX>(dv, x0, x1, rp, st, [&](int64_t n, double s0, double s1) { apply_epilogue(e, n, s0, s1); });
 }
 
 __global__ void k_kron_mode(KronView kv, int m, const double *__restrict__ in, double *__restrict__ out) {
@@ -105,9 +106,27 @@ static inline int ew_grid(sdfs_ctx *ctx, int64_t N) {
 
 static inline int dense_grid(sdfs_ctx *ctx, const DenseView &dv) {
     const int64_t nloc = dv.row_end - dv.row_begin;
-    int64_t g = (nloc + SDFS_WARPS * 4 - 1) / (SDFS_WARPS * 4);
-    const int64_t cap = (int64_t)ctx->sm_count * 2;
+    int64_t g = (nloc + TR - 1) / TR;                 // one CTA per SM sweeps groups of TR rows
+    if (!dv.vec2) g = (g + SDFS_WARPS - 1) / SDFS_WARPS;
+    const int64_t cap = ctx->sm_count;
     return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+template <int NX>
+static int launch_dense_apply(sdfs_ctx *ctx, const DenseView &dv, const double *x0, const double *x1, const EpiArgs &e) {
+    const size_t smem = dv.vec2 ? sizeof(RowPipe<NX>) : 0;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_dense_apply<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(RowPipe<NX>)));
+    const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
+    if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
+    k_dense_apply<NX><<<dense_grid(ctx, dv), SDFS_THREADS, smem, ctx->stream>>>(dv, x0, x1, e);
+    if (prof) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
+        ctx->prof_used += 2;
+    }
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SDFS_OK;
 }
 
 // Shared driver: prologue -> P pass(es) -> epilogue.
@@ -126,10 +145,8 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
     ctx->launches++;
     if (dense) {
         if (op->dv.row_end > op->dv.row_begin) {
-            const int grid = dense_grid(ctx, op->dv);
-            if (nx == 1) k_dense_apply<1><<<grid, SDFS_THREADS, 0, ctx->stream>>>(op->dv, x0, x0, e);
-            else k_dense_apply<2><<<grid, SDFS_THREADS, 0, ctx->stream>>>(op->dv, x0, x1, e);
-            ctx->launches++;
+            if (nx == 1) TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e));
+            else TRY(launch_dense_apply<2>(ctx, op->dv, x0, x1, e));
         }
         CUDA_TRY(ctx, cudaGetLastError());
         if (ctx->nranks > 1) {

@@ -1,19 +1,183 @@
 // Streaming row-tile dot products: the HBM-bound core of every dense operator
-// application  (y = P x with fused prologue/epilogue).
+// application  (s = P x with fused prologue/epilogue).
 //
-// Data layout: P row-major fp64, leading dimension ld (rows 16-byte aligned when
-// ld is even -> 16-byte vector loads; otherwise 8-byte loads).  One warp owns R
-// consecutive rows and walks the columns in 64-column chunks: lane l reads columns
-// 64c+2l, 64c+2l+1 of every row as one 16-byte streaming load (512 contiguous
-// bytes per row per warp instruction), U chunks are issued back to back so each
-// lane keeps R*U independent 16-byte loads in flight.  x comes through L1/L2 with
-// default caching and is shared by the R rows.  Per-lane partial sums are
-// accumulated in a fixed column order and reduced with a fixed xor-shuffle tree,
-// so a row's result is bit-identical for every R, U, grid size and row sharding.
+// Primary path (rows 16-byte aligned): TMA-fed CTA-cooperative rows.
+//   A CTA owns groups of TR = 4 consecutive rows (group g -> CTA g mod grid, so the
+//   whole grid sweeps one compact window of P).  One producer thread streams each
+//   group as [TR rows x TCW = 512 columns] stages with cp.async.bulk (TMA bulk copy,
+//   4 KB contiguous per row) plus the matching 4 KB chunk of x into a TST = 8 deep
+//   shared-memory ring guarded by full/empty mbarriers (128 KB of P in flight per
+//   SM).  8 consumer warps split every stage by 64-column slices (conflict-free
+//   16-byte LDS), accumulate per-lane partials in a fixed column order, and reduce
+//   warp -> CTA in a fixed order.  Measured 7.41 TB/s on an 88 GB P
+//   (profiles/r01_bw_probe.md), ahead of every LDG variant.
+// Fallback path (odd leading dimension / unaligned user P): per-warp rows with
+//   8-byte streaming loads.
+// In both paths a row's result depends only on (N, path), never on the grid size
+// or the row sharding, so multi-GPU runs reproduce single-GPU rows bit for bit.
 #pragma once
 #include "common.cuh"
 
-template <int R, int U, int NX, bool VEC2>
+#define TR 4          // rows per group
+#define TCW 512       // columns per stage
+#define TST 8         // stages in the ring
+#define CONSUMER_WARPS 8
+#define PRODUCER_WARP 8
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Shared-memory ring.  NX = number of x vectors contracted in the same P stream.
+template <int NX>
+struct RowPipe {
+    double P[TST][TR][TCW];          // 128 KB
+    double X[TST][NX][TCW];          // 32 KB per x vector
+    double part[CONSUMER_WARPS][NX][TR];
+    uint64_t full[TST], empty[TST];
+};
+struct PipeState {                   // per-thread ring position, persists across passes
+    int stage;
+    uint32_t phase;
+};
+
+template <int NX>
+__device__ __forceinline__ void pipe_init(RowPipe<NX> *rp, PipeState &st) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TST; ++s) {
+            mbar_init(&rp->full[s], 1);
+            mbar_init(&rp->empty[s], CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    st.stage = 0;
+    st.phase = 0;
+    __syncthreads();
+}
+
+// One pass over this rank's rows with the TMA ring.  Block = 9 warps (8 consumers +
+// 1 producer).  epi(n_global, s0, s1) runs on thread r (< rows in group) of warp 0.
+// Preconditions: dv.vec2 (16-byte aligned rows, ld even), x0/x1 16-byte aligned and
+// readable up to index round_up(N, 2).
+template <int NX, class Epi>
+__device__ __forceinline__ void dense_pass_tma(const DenseView &dv, const double *x0, const double *x1,
+                                               RowPipe<NX> *rp, PipeState &st, Epi &&epi) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nloc = dv.row_end - dv.row_begin;
+    const int64_t ngroups = (nloc + TR - 1) / TR;
+    const int64_t ncols = (dv.N + 1) & ~(int64_t)1;          // even number of columns to move (ld >= ncols)
+    const int64_t nck = (ncols + TCW - 1) / TCW;
+    if (warp == PRODUCER_WARP) {
+        if (lane == 0) {
+            // order the generic-proxy stores that produced x (before the last grid barrier)
+            // ahead of the async-proxy reads below
+            asm volatile("fence.proxy.async;" ::: "memory");
+            for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+                const int64_t r0 = g * TR;
+                const int nr = (int)(nloc - r0 < TR ? nloc - r0 : TR);
+                const double *p0 = dv.P + r0 * dv.ld;
+                for (int64_t cb = 0; cb < nck; ++cb) {
+                    const int64_t col = cb * TCW;
+                    const uint32_t bytes = (uint32_t)((ncols - col < TCW ? ncols - col : TCW) * 8);
+                    mbar_wait(&rp->empty[st.stage], st.phase ^ 1);
+                    mbar_expect_tx(&rp->full[st.stage], bytes * (uint32_t)(nr + NX));
+                    for (int r = 0; r < nr; ++r)
+                        bulk_g2s(&rp->P[st.stage][r][0], p0 + (int64_t)r * dv.ld + col, bytes, &rp->full[st.stage]);
+                    bulk_g2s(&rp->X[st.stage][0][0], x0 + col, bytes, &rp->full[st.stage]);
+                    if (NX > 1) bulk_g2s(&rp->X[st.stage][NX - 1][0], x1 + col, bytes, &rp->full[st.stage]);
+                    if (++st.stage == TST) { st.stage = 0; st.phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+            const int64_t r0 = g * TR;
+            const int nr = (int)(nloc - r0 < TR ? nloc - r0 : TR);
+            double a[NX][TR][2];
+#pragma unroll
+            for (int q = 0; q < NX; ++q)
+#pragma unroll
+                for (int r = 0; r < TR; ++r) a[q][r][0] = a[q][r][1] = 0.0;
+            for (int64_t cb = 0; cb < nck; ++cb) {
+                const int64_t col = cb * TCW;
+                const int wcols = (int)(ncols - col < TCW ? ncols - col : TCW);
+                mbar_wait(&rp->full[st.stage], st.phase);
+                // slice `warp` of the stage: columns [64 warp, 64 warp + 64); lane takes 2 of them.
+                // Rows beyond nr hold stale data: computed, never used.
+                const int cc = warp * 64 + 2 * lane;
+                if (cc < wcols) {
+                    double2 xv[NX];
+                    xv[0] = *reinterpret_cast<const double2 *>(&rp->X[st.stage][0][cc]);
+                    if (NX > 1) xv[NX - 1] = *reinterpret_cast<const double2 *>(&rp->X[st.stage][NX - 1][cc]);
+                    // odd N: column N is padding (moved only to keep 16-byte granularity)
+                    const bool pad_y = (col + cc + 1 >= dv.N);
+                    if (pad_y) {
+                        xv[0].y = 0.0;
+                        if (NX > 1) xv[NX - 1].y = 0.0;
+                    }
+#pragma unroll
+                    for (int r = 0; r < TR; ++r) {
+                        double2 pv = *reinterpret_cast<const double2 *>(&rp->P[st.stage][r][cc]);
+                        if (pad_y) pv.y = 0.0;
+#pragma unroll
+                        for (int q = 0; q < NX; ++q) {
+                            a[q][r][0] = fma(pv.x, xv[q].x, a[q][r][0]);
+                            a[q][r][1] = fma(pv.y, xv[q].y, a[q][r][1]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&rp->empty[st.stage]);
+                if (++st.stage == TST) { st.stage = 0; st.phase ^= 1; }
+            }
+#pragma unroll
+            for (int q = 0; q < NX; ++q)
+#pragma unroll
+                for (int r = 0; r < TR; ++r) {
+                    const double s = warp_sum(a[q][r][0] + a[q][r][1]);
+                    if (lane == 0) rp->part[warp][q][r] = s;
+                }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x < nr) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int w = 0; w < CONSUMER_WARPS; ++w) {
+                    s0 += rp->part[w][0][threadIdx.x];
+                    if (NX > 1) s1 += rp->part[w][NX - 1][threadIdx.x];
+                }
+                epi(dv.row_begin + r0 + threadIdx.x, s0, NX > 1 ? s1 : s0);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Fallback: per-warp rows with direct streaming loads (any alignment).
+// ---------------------------------------------------------------------------
+template <int R, int U, int NX>
 __device__ __forceinline__ void warp_rows_dot(const double *__restrict__ p0, int64_t ld,
                                               const double *x0, const double *x1, int64_t N,
                                               double (&out)[NX][R]) {
@@ -23,13 +187,11 @@ __device__ __forceinline__ void warp_rows_dot(const double *__restrict__ p0, int
     for (int q = 0; q < NX; ++q)
 #pragma unroll
         for (int r = 0; r < R; ++r) a[q][r][0] = a[q][r][1] = 0.0;
-
     const double *pr[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) pr[r] = p0 + (int64_t)r * ld + 2 * lane;
     const double *xa = x0 + 2 * lane;
     const double *xb = (NX > 1) ? (x1 + 2 * lane) : xa;
-
     const int64_t nfull = N >> 6;
     int64_t c = 0;
     for (; c + U <= nfull; c += U) {
@@ -40,13 +202,12 @@ __device__ __forceinline__ void warp_rows_dot(const double *__restrict__ p0, int
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const double *p = pr[r] + ((c + u) << 6);
-                if (VEC2) pv[u][r] = ld_stream2(p);
-                else pv[u][r] = make_double2(ld_stream1(p), ld_stream1(p + 1));
+                pv[u][r] = make_double2(ld_stream1(p), ld_stream1(p + 1));
             }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            xv[0][u] = ld_x2(xa + ((c + u) << 6));
-            if (NX > 1) xv[NX - 1][u] = ld_x2(xb + ((c + u) << 6));
+            xv[0][u] = make_double2(ld_x1(xa + ((c + u) << 6)), ld_x1(xa + ((c + u) << 6) + 1));
+            if (NX > 1) xv[NX - 1][u] = make_double2(ld_x1(xb + ((c + u) << 6)), ld_x1(xb + ((c + u) << 6) + 1));
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -59,23 +220,19 @@ __device__ __forceinline__ void warp_rows_dot(const double *__restrict__ p0, int
                 }
     }
     for (; c < nfull; ++c) {
-        double2 pv[R];
+        double2 xv[NX];
+        xv[0] = make_double2(ld_x1(xa + (c << 6)), ld_x1(xa + (c << 6) + 1));
+        if (NX > 1) xv[NX - 1] = make_double2(ld_x1(xb + (c << 6)), ld_x1(xb + (c << 6) + 1));
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const double *p = pr[r] + (c << 6);
-            if (VEC2) pv[r] = ld_stream2(p);
-            else pv[r] = make_double2(ld_stream1(p), ld_stream1(p + 1));
-        }
-        double2 xv[NX];
-        xv[0] = ld_x2(xa + (c << 6));
-        if (NX > 1) xv[NX - 1] = ld_x2(xb + (c << 6));
-#pragma unroll
-        for (int r = 0; r < R; ++r)
+            const double2 pv = make_double2(ld_stream1(p), ld_stream1(p + 1));
 #pragma unroll
             for (int q = 0; q < NX; ++q) {
-                a[q][r][0] = fma(pv[r].x, xv[q].x, a[q][r][0]);
-                a[q][r][1] = fma(pv[r].y, xv[q].y, a[q][r][1]);
+                a[q][r][0] = fma(pv.x, xv[q].x, a[q][r][0]);
+                a[q][r][1] = fma(pv.y, xv[q].y, a[q][r][1]);
             }
+        }
     }
     // ragged tail: columns [64*nfull, N)
     const int64_t col = (nfull << 6) + 2 * lane;
@@ -106,7 +263,6 @@ __device__ __forceinline__ void warp_rows_dot(const double *__restrict__ p0, int
         for (int r = 0; r < R; ++r) out[q][r] = warp_sum(a[q][r][0] + a[q][r][1]);
 }
 
-// Select the value belonging to lane `lane` (< R) out of a register array.
 template <int R>
 __device__ __forceinline__ double pick(const double (&v)[R], int lane) {
     double s = v[0];
@@ -116,36 +272,46 @@ __device__ __forceinline__ double pick(const double (&v)[R], int lane) {
     return s;
 }
 
-// One pass over this rank's rows.  Warp `wg` of `nw` owns the contiguous row range
-// [nloc*wg/nw, nloc*(wg+1)/nw); groups of 4 rows, then 2, then 1, so no lane ever
-// touches an invalid row.  epi(n_global, s0, s1) runs on one lane per row.
+// Warp `wg` of `nw` owns row groups wg, wg+nw, ... (groups of 4 rows; the ragged last
+// group is finished with 2- and 1-row passes).  epi runs on one lane per row.
 template <int NX, class Epi>
-__device__ __forceinline__ void dense_rows_pass(const DenseView &dv, const double *x0,
-                                                const double *x1, int wg, int nw,
-                                                Epi &&epi) {
+__device__ __forceinline__ void dense_pass_ldg(const DenseView &dv, const double *x0, const double *x1,
+                                               int wg, int nw, Epi &&epi) {
     const int lane = threadIdx.x & 31;
     const int64_t nloc = dv.row_end - dv.row_begin;
-    int64_t r = nloc * wg / nw;
-    const int64_t r1 = nloc * (wg + 1) / nw;
-    constexpr int R4U = (NX == 1) ? 4 : 2;
-    for (; r + 4 <= r1; r += 4) {
-        double s[NX][4];
-        if (dv.vec2) warp_rows_dot<4, R4U, NX, true>(dv.P + r * dv.ld, dv.ld, x0, x1, dv.N, s);
-        else warp_rows_dot<4, R4U, NX, false>(dv.P + r * dv.ld, dv.ld, x0, x1, dv.N, s);
-        if (lane < 4) epi(dv.row_begin + r + lane, pick<4>(s[0], lane), pick<4>(s[NX - 1], lane));
+    const int64_t ngroups = (nloc + 3) / 4;
+    for (int64_t g = wg; g < ngroups; g += nw) {
+        int64_t r = g * 4;
+        const int64_t r1 = (r + 4 < nloc) ? r + 4 : nloc;
+        if (r + 4 <= r1) {
+            double s[NX][4];
+            warp_rows_dot<4, 4, NX>(dv.P + r * dv.ld, dv.ld, x0, x1, dv.N, s);
+            if (lane < 4) epi(dv.row_begin + r + lane, pick<4>(s[0], lane), pick<4>(s[NX - 1], lane));
+            continue;
+        }
+        if (r + 2 <= r1) {
+            double s[NX][2];
+            warp_rows_dot<2, 4, NX>(dv.P + r * dv.ld, dv.ld, x0, x1, dv.N, s);
+            if (lane < 2) epi(dv.row_begin + r + lane, pick<2>(s[0], lane), pick<2>(s[NX - 1], lane));
+            r += 2;
+        }
+        if (r < r1) {
+            double s[NX][1];
+            warp_rows_dot<1, 8, NX>(dv.P + r * dv.ld, dv.ld, x0, x1, dv.N, s);
+            if (lane < 1) epi(dv.row_begin + r, s[0][0], s[NX - 1][0]);
+        }
     }
-    if (r + 2 <= r1) {
-        double s[NX][2];
-        if (dv.vec2) warp_rows_dot<2, 4, NX, true>(dv.P + r * dv.ld, dv.ld, x0, x1, dv.N, s);
-        else warp_rows_dot<2, 4, NX, false>(dv.P + r * dv.ld, dv.ld, x0, x1, dv.N, s);
-        if (lane < 2) epi(dv.row_begin + r + lane, pick<2>(s[0], lane), pick<2>(s[NX - 1], lane));
-        r += 2;
-    }
-    if (r < r1) {
-        double s[NX][1];
-        if (dv.vec2) warp_rows_dot<1, 8, NX, true>(dv.P + r * dv.ld, dv.ld, x0, x1, dv.N, s);
-        else warp_rows_dot<1, 8, NX, false>(dv.P + r * dv.ld, dv.ld, x0, x1, dv.N, s);
-        if (lane < 1) epi(dv.row_begin + r, s[0][0], s[NX - 1][0]);
+}
+
+// Dispatch on the operator's alignment class.
+template <int NX, class Epi>
+__device__ __forceinline__ void dense_pass(const DenseView &dv, const double *x0, const double *x1,
+                                           RowPipe<NX> *rp, PipeState &st, Epi &&epi) {
+    if (dv.vec2) {
+        dense_pass_tma<NX>(dv, x0, x1, rp, st, epi);
+    } else {
+        const int wg = blockIdx.x * SDFS_WARPS + (threadIdx.x >> 5);
+        dense_pass_ldg<NX>(dv, x0, x1, wg, gridDim.x * SDFS_WARPS, epi);
     }
 }
 
@@ -154,8 +320,7 @@ __device__ __forceinline__ void dense_rows_pass(const DenseView &dv, const doubl
 // over a grid-stride range of output elements.  Called once per mode with a grid
 // barrier between calls; the last mode feeds the epilogue instead of storing.
 template <class Sink>
-__device__ __forceinline__ void kron_mode_pass(const KronView &kv, int m,
-                                               const double *__restrict__ in, int64_t tid,
+__device__ __forceinline__ void kron_mode_pass(const KronView &kv, int m, const double *in, int64_t tid,
                                                int64_t nthreads, Sink &&sink) {
     const KronMode &md = kv.modes[m];
     const int dim = md.dim;

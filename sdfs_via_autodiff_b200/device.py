@@ -79,6 +79,15 @@ class Context:
     def launch_count(self):
         return int(lib.sdfs_ctx_launch_count(self.handle))
 
+    def prof_enable(self, max_launches):
+        check(lib.sdfs_prof_enable(self.handle, int(max_launches)), self.handle)
+
+    def prof_read(self):
+        """(total device ms, launches) of the dense-pass kernel since prof_enable."""
+        ms, n = C.c_double(), C.c_int64()
+        check(lib.sdfs_prof_read(self.handle, C.byref(ms), C.byref(n)), self.handle)
+        return ms.value, n.value
+
     def timer_start(self):
         check(lib.sdfs_timer_start(self.handle), self.handle)
 

@@ -260,8 +260,10 @@ def test_ssy_10k_states_dense_vs_kron_and_counts():
     res = S.solve_ssy(S.SSY(), shapes, algo="newton", storage="dense", tol=1e-9, bicgstab_atol=1e-10,
                       krylov_rtol=1e-12)
     assert np.max(np.abs(np.asarray(res.euler))) < 1e-8
-    qf = np.asarray(res.q_f)
-    assert 0.99 < qf.min() and qf.max() < 1.01
+    from oracle.sdf import e_sdf_ssy as _es
+    P, ar, ac, β, θ = O.dense_ssy(shapes, ssy.params, arrays)
+    qf_ref, _ = O.sdf_dense(np.asarray(res.w), P, ar, ac, _es(shapes, ssy.params, arrays), β, θ)
+    np.testing.assert_allclose(np.asarray(res.q_f).reshape(-1), qf_ref, rtol=RTOL_W)
 
 
 def test_dlpack_roundtrip_with_torch():
