@@ -249,7 +249,9 @@ def run_ours(args, shapes):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("k_dense_apply_bytes_per_launch")
+            tj = json.load(open(tp))
+            if tj.get("shapes") == list(shapes) and tj.get("n_gpus") == world:
+                traffic = tj.get("k_dense_apply_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

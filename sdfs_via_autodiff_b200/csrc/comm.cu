@@ -185,6 +185,7 @@ int sdfs_comm_arena_export(sdfs_ctx *ctx, int64_t max_N, void *h_handle64) {
     cs->arena_maxN = max_N;
     CUDA_TRY(ctx, cudaMalloc(&cs->arena, cs->arena_bytes));
     CUDA_TRY(ctx, cudaMemset(cs->arena, 0, cs->arena_bytes));
+    CUDA_TRY(ctx, cudaDeviceSynchronize());   // zeroed before any peer can see the handle
     cudaIpcMemHandle_t h;
     CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, cs->arena));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");

@@ -1,0 +1,68 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU):
+row-sharded dense operator vs the oracle; NCCL all-gather path for single applications,
+fused peer-store path for the device-resident SA / Newton loops."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch.distributed as dist
+import oracle as O
+import sdfs_via_autodiff_b200 as S
+from sdfs_via_autodiff_b200 import dist as sd
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+dist.init_process_group("gloo", init_method="env://")
+ctx = S.Context(local)
+S.Context._default = ctx
+sd.init_comm(ctx, rank, world, dist, max_N=120000)
+ok = True
+
+
+def report(name, cond, extra=""):
+    global ok
+    ok = ok and bool(cond)
+    if rank == 0:
+        print(("PASS " if cond else "FAIL ") + name + " " + extra, flush=True)
+
+
+ssy = O.SSY()
+for shapes in ((2, 3, 4, 5), (7, 5, 6, 9), (10, 10, 10, 10)):
+    arrays = O.discretize_ssy(ssy, shapes)
+    kop = O.KronSSY(shapes, ssy.params, arrays)
+    op = S.make_T_ssy(S.SSY(), shapes, storage="dense", ctx=ctx)
+    N = op.N
+    report(f"{shapes} row slice", (op.row_begin, op.row_end) == sd.row_partition(N, world, rank),
+           f"rank0 rows [{op.row_begin},{op.row_end})")
+    rng = np.random.default_rng(1233)
+    w = np.exp(rng.standard_normal(shapes))
+    got = np.asarray(op(w))
+    report(f"{shapes} T (NCCL all-gather)", np.allclose(got, kop.T(w), rtol=1e-12, atol=0))
+    v = rng.standard_normal(shapes)
+    report(f"{shapes} JVP", np.allclose(np.asarray(op.jvp(w, v)), kop.jvp(w, v), rtol=1e-10, atol=1e-12))
+    t0 = time.time()
+    ws, k = S.successive_approx(op, np.full(shapes, 800.0), verbose=False)
+    dt = time.time() - t0
+    w_ref, k_ref = O.successive_approx(kop.T, np.full(shapes, 800.0), verbose=False)
+    report(f"{shapes} SA fused loop", abs(k - k_ref) <= 1 and np.allclose(np.asarray(ws), w_ref, rtol=1e-10),
+           f"iters {k} vs {k_ref}, {dt:.2f}s, {dt / max(k, 1) * 1e6:.1f} us/iter")
+    t0 = time.time()
+    wn, kn, info = S.newton_solver(op, np.full(shapes, 800.0), verbose=False, return_info=True)
+    dt = time.time() - t0
+    wn_ref, kn_ref = O.newton_solver(kop.T, np.full(shapes, 800.0), jvp=kop.jvp, verbose=False)
+    report(f"{shapes} Newton fused loop", abs(kn - kn_ref) <= 1 and np.allclose(np.asarray(wn), wn_ref, rtol=1e-5),
+           f"outer {kn} vs {kn_ref}, inner {info['inner_iters']}, {dt:.2f}s")
+    wt, kt = S.newton_solver(op, np.full(shapes, 800.0), tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12, verbose=False)
+    wfix, _ = O.successive_approx(kop.T, wn_ref, tol=1e-11, verbose=False)
+    report(f"{shapes} Newton tight", np.allclose(np.asarray(wt), wfix, rtol=1e-10))
+    wg, kg = S.newton_solver(op, np.full(shapes, 800.0), krylov="gmres", tol=1e-9, bicgstab_atol=1e-10,
+                             krylov_rtol=1e-12, verbose=False)
+    report(f"{shapes} Newton GMRES", np.allclose(np.asarray(wg), wfix, rtol=1e-10))
+    q, e = op.sdf(wt)
+    report(f"{shapes} SDF euler", np.max(np.abs(np.asarray(e))) < 1e-8)
+    del op
+flag = [ok]
+allok = [None] * world
+dist.all_gather_object(allok, ok)
+if rank == 0:
+    print("ALL PASS" if all(allok) else f"SOME FAILED {allok}", flush=True)
+dist.barrier()
+dist.destroy_process_group()
