@@ -44,7 +44,7 @@ typedef struct sdfs_factors sdfs_factors; /* discretised model: Markov factor ar
 
 enum { SDFS_MODEL_SSY = 0, SDFS_MODEL_GCY = 1 };
 enum { SDFS_KRYLOV_BICGSTAB = 0, SDFS_KRYLOV_GMRES = 1 };
-enum { SDFS_STORAGE_DENSE = 0, SDFS_STORAGE_KRON = 1 };
+enum { SDFS_STORAGE_DENSE = 0, SDFS_STORAGE_KRON = 1, SDFS_STORAGE_DENSE_REPLICATED = 2 };
 
 /* ---- context ---------------------------------------------------------- */
 int sdfs_abi_version(void);
@@ -114,7 +114,8 @@ int sdfs_op_from_dense(sdfs_ctx *ctx, const double *d_P, int64_t N, int64_t ld,
 /* Expand the factors into a dense P (device kernel) or keep them in factor form
  * (storage = SDFS_STORAGE_KRON: sum-factorised apply, T_ssy ssy_wc_ratio.py:82-149,
  * T_gcy gcy_wc_ratio.py:134-236).  Dense storage honours the context's rank:
- * each rank materialises only its row slice. */
+ * each rank materialises only its row slice; SDFS_STORAGE_DENSE_REPLICATED keeps the
+ * full P on every rank (parameter sweeps shard columns, not rows). */
 int sdfs_op_from_factors(sdfs_ctx *ctx, sdfs_factors *f, int storage, sdfs_op **out);
 int sdfs_op_destroy(sdfs_op *op);
 int sdfs_op_info(sdfs_op *op, int64_t *N, int64_t *ld, int64_t *row_begin,

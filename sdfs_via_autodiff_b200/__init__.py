@@ -16,3 +16,4 @@ from .gcy_wc_ratio import discretize_gcy, T_gcy, make_T_gcy, test_compute_wc_rat
 from .solvers import (successive_approx, newton_solver, solver, solvers,                 # noqa: F401
                       default_tolerance, default_max_iter)
 from .sdf import solve_ssy, solve_gcy, SDFResult                 # noqa: F401
+from .sweep import make_sweep_operator, sweep_apply_T, sweep_solve                      # noqa: F401

@@ -25,6 +25,8 @@ void *comm_peer_arena(sdfs_ctx *ctx, int r);
 int64_t comm_arena_maxN(sdfs_ctx *ctx);
 unsigned long long *comm_epoch(sdfs_ctx *ctx);
 int comm_allgather_rows(sdfs_ctx *ctx, double *d_vec, int64_t N);
+int small_sa_try(sdfs_op *op, const double *d_w_init, double tol, int64_t max_iter, double *d_w_out,
+                 double *d_err_hist, int64_t hist_stride, int64_t hist_cap);   // small.cu
 
 #define TRY(x) do { int _rc = (x); if (_rc != SDFS_OK) return _rc; } while (0)
 
@@ -664,7 +666,11 @@ static int build_env(sdfs_op *op, LoopEnv *env) {
     env->nranks = ctx->nranks;
     env->status = (LoopStatus *)ctx->d_status;
     const int64_t N = (op->storage == SDFS_STORAGE_DENSE) ? op->dv.N : op->kv.N;
-    if (ctx->nranks == 1) {
+    const bool sharded = ctx->nranks > 1 && op->storage == SDFS_STORAGE_DENSE &&
+                         (op->dv.row_end - op->dv.row_begin) < op->dv.N;
+    if (!sharded) {   // single GPU, factor form, or a replicated dense operator: purely local loop
+        env->rank = 0;
+        env->nranks = 1;
         if (!op->slots) {
             CUDA_TRY(ctx, cudaMalloc(&op->slots, arena_slots_doubles() * sizeof(double)));
             CUDA_TRY(ctx, cudaMemsetAsync(op->slots, 0, arena_slots_doubles() * sizeof(double), ctx->stream));
@@ -675,8 +681,6 @@ static int build_env(sdfs_op *op, LoopEnv *env) {
         env->flags[0] = nullptr;
         env->epoch0 = 0;
     } else {
-        if (op->storage != SDFS_STORAGE_DENSE)
-            return sdfs_set_error(ctx, SDFS_ERR_UNSUPPORTED, "factor-form operators run on one GPU (vectors of 8N bytes do not need sharding)");
         if (!comm_peers_ready(ctx))
             return sdfs_set_error(ctx, SDFS_ERR_COMM, "multi-GPU solver loops need the exchange arena (sdfs_comm_arena_export/import)");
         if (comm_arena_maxN(ctx) < N)
@@ -689,14 +693,14 @@ static int build_env(sdfs_op *op, LoopEnv *env) {
 }
 
 template <class Kern>
-static int coop_grid(sdfs_ctx *ctx, Kern kern, size_t dyn_smem, int max_per_sm, int64_t work_groups, int *grid_out) {
+static int coop_grid(sdfs_ctx *ctx, Kern kern, size_t dyn_smem, int max_per_sm, int64_t work_groups, bool force_full, int *grid_out) {
     if (dyn_smem > 0) CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     int per_sm = 0;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SDFS_THREADS, dyn_smem));
     if (per_sm < 1) return sdfs_set_error(ctx, SDFS_ERR_CUDA, "cooperative kernel does not fit on an SM");
     if (per_sm > max_per_sm) per_sm = max_per_sm;
     int64_t grid = (int64_t)per_sm * ctx->sm_count;
-    if (ctx->nranks == 1) {   // small problems: fewer CTAs make the grid barrier cheaper
+    if (!force_full) {   // small problems: fewer CTAs make the grid barrier cheaper
         int64_t want = work_groups < 1 ? 1 : work_groups;
         if (want < grid) grid = want;
     }
@@ -734,6 +738,18 @@ int sdfs_solve_sa(sdfs_op *op, const double *d_w_init, double tol, int64_t max_i
     LoopEnv env;
     TRY(build_env(op, &env));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(LoopStatus), ctx->stream));
+    if (env.nranks == 1) {
+        // reference-sized grids: whole solve in one CTA with P resident in shared memory
+        const int handled = small_sa_try(op, d_w_init, tol, max_iter, d_w_out, d_err_hist, hist_stride, hist_cap);
+        if (handled < 0) return handled;
+        if (handled == 1) {
+            LoopStatus *hs0 = (LoopStatus *)ctx->h_status;
+            TRY(finish_loop(ctx, hs0, 0));
+            if (iters) *iters = hs0->iters;
+            if (final_err) *final_err = hs0->final_err;
+            return SDFS_OK;
+        }
+    }
     SAArgs a{};
     a.w_init = d_w_init;
     a.w[0] = op->work + 2 * op->ldv;
@@ -748,7 +764,7 @@ int sdfs_solve_sa(sdfs_op *op, const double *d_w_init, double tol, int64_t max_i
     const bool dense = op->storage == SDFS_STORAGE_DENSE;
     if (dense) {
         DenseLoopOp lop{op->dv};
-        TRY(coop_grid(ctx, k_sa_loop<DenseLoopOp>, lop.dyn_smem(), 1, dense_groups(op->dv), &grid));
+        TRY(coop_grid(ctx, k_sa_loop<DenseLoopOp>, lop.dyn_smem(), 1, dense_groups(op->dv), env.nranks > 1, &grid));
         void *args[] = {&lop, &a, &env};
         CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sa_loop<DenseLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, lop.dyn_smem(), ctx->stream));
     } else {
@@ -757,14 +773,14 @@ int sdfs_solve_sa(sdfs_op *op, const double *d_w_init, double tol, int64_t max_i
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)op->kv.N * sizeof(double)));
         }
         KronLoopOp lop{op->kv, op->kron_tmp[0], op->kron_tmp[1]};
-        TRY(coop_grid(ctx, k_sa_loop<KronLoopOp>, 0, 2, (op->kv.N + SDFS_THREADS - 1) / SDFS_THREADS, &grid));
+        TRY(coop_grid(ctx, k_sa_loop<KronLoopOp>, 0, 2, (op->kv.N + SDFS_THREADS - 1) / SDFS_THREADS, false, &grid));
         void *args[] = {&lop, &a, &env};
         CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sa_loop<KronLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, 0, ctx->stream));
     }
     ctx->launches++;
     LoopStatus *hs = (LoopStatus *)ctx->h_status;
     TRY(finish_loop(ctx, hs, 0));
-    if (ctx->nranks > 1) {
+    if (env.nranks > 1) {
         *comm_epoch(ctx) = hs->epoch_end;   // every rank passed the same barriers
         TRY(comm_allgather_rows(ctx, d_w_out, op->dv.N));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -807,7 +823,7 @@ int sdfs_solve_newton(sdfs_op *op, const double *d_w_init, double tol, int64_t m
     int grid = 0;
     if (dense) {
         DenseLoopOp lop{op->dv};
-        TRY(coop_grid(ctx, k_newton_loop<DenseLoopOp>, lop.dyn_smem(), 1, dense_groups(op->dv), &grid));
+        TRY(coop_grid(ctx, k_newton_loop<DenseLoopOp>, lop.dyn_smem(), 1, dense_groups(op->dv), env.nranks > 1, &grid));
         void *args[] = {&lop, &a, &env};
         CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_newton_loop<DenseLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, lop.dyn_smem(), ctx->stream));
     } else {
@@ -816,14 +832,14 @@ int sdfs_solve_newton(sdfs_op *op, const double *d_w_init, double tol, int64_t m
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)N * sizeof(double)));
         }
         KronLoopOp lop{op->kv, op->kron_tmp[0], op->kron_tmp[1]};
-        TRY(coop_grid(ctx, k_newton_loop<KronLoopOp>, 0, 2, (N + SDFS_THREADS - 1) / SDFS_THREADS, &grid));
+        TRY(coop_grid(ctx, k_newton_loop<KronLoopOp>, 0, 2, (N + SDFS_THREADS - 1) / SDFS_THREADS, false, &grid));
         void *args[] = {&lop, &a, &env};
         CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_newton_loop<KronLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, 0, ctx->stream));
     }
     ctx->launches++;
     LoopStatus *hs = (LoopStatus *)ctx->h_status;
     TRY(finish_loop(ctx, hs, 0));
-    if (ctx->nranks > 1) {
+    if (env.nranks > 1) {
         *comm_epoch(ctx) = hs->epoch_end;   // every rank passed the same barriers
         TRY(comm_allgather_rows(ctx, d_w_out, N));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -149,7 +149,7 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
             else TRY(launch_dense_apply<2>(ctx, op->dv, x0, x1, e));
         }
         CUDA_TRY(ctx, cudaGetLastError());
-        if (ctx->nranks > 1) {
+        if (ctx->nranks > 1 && op->dv.row_end - op->dv.row_begin < N) {
             if (gather0 && e.out0) TRY(comm_allgather_rows(ctx, e.out0, N));
             if (gather1 && e.out1) TRY(comm_allgather_rows(ctx, e.out1, N));
         }
@@ -205,7 +205,9 @@ int sdfs_op_from_dense(sdfs_ctx *ctx, const double *d_P, int64_t N, int64_t ld, 
 
 int sdfs_op_from_factors(sdfs_ctx *ctx, sdfs_factors *f, int storage, sdfs_op **out) {
     ARG_CHECK(ctx, ctx && f && out && f->ctx == ctx);
-    ARG_CHECK(ctx, storage == SDFS_STORAGE_DENSE || storage == SDFS_STORAGE_KRON);
+    ARG_CHECK(ctx, storage == SDFS_STORAGE_DENSE || storage == SDFS_STORAGE_KRON || storage == SDFS_STORAGE_DENSE_REPLICATED);
+    const bool replicated = storage == SDFS_STORAGE_DENSE_REPLICATED;
+    if (replicated) storage = SDFS_STORAGE_DENSE;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     sdfs_op *op = new sdfs_op();
     op->ctx = ctx;
@@ -237,6 +239,7 @@ int sdfs_op_from_factors(sdfs_ctx *ctx, sdfs_factors *f, int storage, sdfs_op **
         int64_t rb = chunk * ctx->rank, re = rb + chunk;
         if (rb > N) rb = N;
         if (re > N) re = N;
+        if (replicated) { rb = 0; re = N; }
         const size_t bytes = (size_t)(re - rb > 0 ? re - rb : 1) * ld * sizeof(double);
         if ((e = cudaMalloc(&op->own_P, bytes)) != cudaSuccess) {
             rc = sdfs_set_error(ctx, SDFS_ERR_NOMEM,

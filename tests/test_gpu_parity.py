@@ -266,6 +266,39 @@ def test_ssy_10k_states_dense_vs_kron_and_counts():
     np.testing.assert_allclose(np.asarray(res.q_f).reshape(-1), qf_ref, rtol=RTOL_W)
 
 
+def test_sweep_batched_T_and_solve():
+    """BASELINE config 5 in miniature: B parameter sets through the fp64 tensor-core GEMM."""
+    shapes = (4, 7, 6, 5)
+    base = O.SSY()
+    arrays = O.discretize_ssy(base, shapes)          # P does not depend on (γ, ψ, β)
+    prefs = np.array([[8.89, 1.97, 0.999], [5.0, 1.3, 0.997], [12.0, 2.0, 0.999], [7.3, 1.61, 0.998],
+                      [10.0, 1.5, 0.9985]])
+    op = S.make_sweep_operator(S.SSY(), shapes)
+    rng = np.random.default_rng(11)
+    W = 300 + 600 * rng.random((len(prefs),) + shapes)
+    got = np.asarray(S.sweep_apply_T(op, prefs, W))
+    for b, (γ, ψ, β) in enumerate(prefs):
+        m = O.SSY(γ=γ, ψ=ψ, β=β)
+        ref = O.KronSSY(shapes, m.params, arrays).T(W[b])
+        np.testing.assert_allclose(got[b], ref, rtol=RTOL_T)
+    # ragged sizes: N = 120 (one partial row tile), B = 3 (partial column tile)
+    shapes = (2, 3, 4, 5)
+    arrays = O.discretize_ssy(base, shapes)
+    op = S.make_sweep_operator(S.SSY(), shapes)
+    Wd, iters, errs = S.sweep_solve(op, prefs[:3], w_init=800.0, tol=1e-7)
+    Wn = np.asarray(Wd)
+    for b, (γ, ψ, β) in enumerate(prefs[:3]):
+        m = O.SSY(γ=γ, ψ=ψ, β=β)
+        kop = O.KronSSY(shapes, m.params, arrays)
+        w_ref, k_ref = O.successive_approx(kop.T, np.full(shapes, 800.0), verbose=False)
+        assert abs(int(iters[b]) - k_ref) <= 1, (b, iters[b], k_ref)
+        np.testing.assert_allclose(Wn[b], w_ref, rtol=RTOL_W)
+        assert errs[b] <= 1e-7
+    # max_iter cap is per column
+    Wd, iters, errs = S.sweep_solve(op, prefs[:2], tol=0.0, max_iter=7)
+    assert list(iters) == [7, 7]
+
+
 def test_dlpack_roundtrip_with_torch():
     torch = pytest.importorskip("torch")
     ctx = S.Context.default()
