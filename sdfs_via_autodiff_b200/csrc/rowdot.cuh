@@ -7,10 +7,11 @@
 //   group as [TR rows x TCW = 512 columns] stages with cp.async.bulk (TMA bulk copy,
 //   4 KB contiguous per row) plus the matching 4 KB chunk of x into a TST = 8 deep
 //   shared-memory ring guarded by full/empty mbarriers (128 KB of P in flight per
-//   SM).  8 consumer warps split every stage by 64-column slices (conflict-free
-//   16-byte LDS), accumulate per-lane partials in a fixed column order, and reduce
-//   warp -> CTA in a fixed order.  Measured 7.41 TB/s on an 88 GB P
-//   (profiles/r01_bw_probe.md), ahead of every LDG variant.
+//   SM).  Ring slot w belongs to consumer warp w, which contracts the whole stage
+//   (conflict-free 16-byte LDS), accumulates per-lane partials in a fixed column
+//   order, and the warps' row partials are combined in a fixed order per row group.
+//   The TMA ring measured 7.41 TB/s on an 88 GB P (profiles/r01_bw_probe.md), ahead
+//   of every LDG variant.
 // Fallback path (odd leading dimension / unaligned user P): per-warp rows with
 //   8-byte streaming loads.
 // In both paths a row's result depends only on (N, path), never on the grid size
@@ -51,29 +52,32 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // Shared-memory ring.  NX = number of x vectors contracted in the same P stream.
+// Ring slot w belongs to consumer warp w: the producer fills slots round-robin, warp w
+// consumes every 8th stage on its own, so a warp has 8 stage-times to turn one stage
+// around (the ring keeps feeding HBM at full rate even when the SM clock drops under the
+// power cap) and a stage is released by a single arrive.
 template <int NX>
 struct RowPipe {
     double P[TST][TR][TCW];          // 128 KB
     double X[TST][NX][TCW];          // 32 KB per x vector
-    double part[CONSUMER_WARPS][NX][TR];
+    double part[2][CONSUMER_WARPS][NX][TR];   // per-warp row partials, double buffered by group
     uint64_t full[TST], empty[TST];
 };
-struct PipeState {                   // per-thread ring position, persists across passes
-    int stage;
-    uint32_t phase;
+struct PipeState {                   // stages issued/consumed by this CTA so far (persists across passes)
+    uint32_t t;
 };
 
 template <int NX>
 __device__ __forceinline__ void pipe_init(RowPipe<NX> *rp, PipeState &st) {
+    static_assert(TST == CONSUMER_WARPS, "one ring slot per consumer warp");
     if (threadIdx.x == 0) {
         for (int s = 0; s < TST; ++s) {
             mbar_init(&rp->full[s], 1);
-            mbar_init(&rp->empty[s], CONSUMER_WARPS);
+            mbar_init(&rp->empty[s], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    st.stage = 0;
-    st.phase = 0;
+    st.t = 0;
     __syncthreads();
 }
 
@@ -88,31 +92,40 @@ __device__ __forceinline__ void dense_pass_tma(const DenseView &dv, const double
     const int64_t nloc = dv.row_end - dv.row_begin;
     const int64_t ngroups = (nloc + TR - 1) / TR;
     const int64_t ncols = (dv.N + 1) & ~(int64_t)1;          // even number of columns to move (ld >= ncols)
-    const int64_t nck = (ncols + TCW - 1) / TCW;
+    const uint32_t nck = (uint32_t)((ncols + TCW - 1) / TCW);
+    const uint32_t t_begin = st.t;
+    // every thread advances the shared stage counter identically
+    const int64_t my_groups = (ngroups > (int64_t)blockIdx.x) ? (ngroups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    st.t = t_begin + (uint32_t)my_groups * nck;
     if (warp == PRODUCER_WARP) {
         if (lane == 0) {
             // order the generic-proxy stores that produced x (before the last grid barrier)
             // ahead of the async-proxy reads below
             asm volatile("fence.proxy.async;" ::: "memory");
+            uint32_t t = t_begin;
             for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
                 const int64_t r0 = g * TR;
                 const int nr = (int)(nloc - r0 < TR ? nloc - r0 : TR);
                 const double *p0 = dv.P + r0 * dv.ld;
-                for (int64_t cb = 0; cb < nck; ++cb) {
-                    const int64_t col = cb * TCW;
+                for (uint32_t cb = 0; cb < nck; ++cb, ++t) {
+                    const int64_t col = (int64_t)cb * TCW;
                     const uint32_t bytes = (uint32_t)((ncols - col < TCW ? ncols - col : TCW) * 8);
-                    mbar_wait(&rp->empty[st.stage], st.phase ^ 1);
-                    mbar_expect_tx(&rp->full[st.stage], bytes * (uint32_t)(nr + NX));
+                    const int slot = t & (TST - 1);
+                    mbar_wait(&rp->empty[slot], ((t >> 3) & 1) ^ 1);
+                    mbar_expect_tx(&rp->full[slot], bytes * (uint32_t)(nr + NX));
                     for (int r = 0; r < nr; ++r)
-                        bulk_g2s(&rp->P[st.stage][r][0], p0 + (int64_t)r * dv.ld + col, bytes, &rp->full[st.stage]);
-                    bulk_g2s(&rp->X[st.stage][0][0], x0 + col, bytes, &rp->full[st.stage]);
-                    if (NX > 1) bulk_g2s(&rp->X[st.stage][NX - 1][0], x1 + col, bytes, &rp->full[st.stage]);
-                    if (++st.stage == TST) { st.stage = 0; st.phase ^= 1; }
+                        bulk_g2s(&rp->P[slot][r][0], p0 + (int64_t)r * dv.ld + col, bytes, &rp->full[slot]);
+                    bulk_g2s(&rp->X[slot][0][0], x0 + col, bytes, &rp->full[slot]);
+                    if (NX > 1) bulk_g2s(&rp->X[slot][NX - 1][0], x1 + col, bytes, &rp->full[slot]);
                 }
             }
         }
     } else {
-        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        uint32_t t0 = t_begin;                   // stage number of column block 0 of the current group
+        int buf = 0;
+        const double *sp = &rp->P[warp][0][0];
+        const double *sx = &rp->X[warp][0][0];
+        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x, t0 += nck, buf ^= 1) {
             const int64_t r0 = g * TR;
             const int nr = (int)(nloc - r0 < TR ? nloc - r0 : TR);
             double a[NX][TR][2];
@@ -120,57 +133,78 @@ __device__ __forceinline__ void dense_pass_tma(const DenseView &dv, const double
             for (int q = 0; q < NX; ++q)
 #pragma unroll
                 for (int r = 0; r < TR; ++r) a[q][r][0] = a[q][r][1] = 0.0;
-            for (int64_t cb = 0; cb < nck; ++cb) {
-                const int64_t col = cb * TCW;
-                const int wcols = (int)(ncols - col < TCW ? ncols - col : TCW);
-                mbar_wait(&rp->full[st.stage], st.phase);
-                // slice `warp` of the stage: columns [64 warp, 64 warp + 64); lane takes 2 of them.
-                // Rows beyond nr hold stale data: computed, never used.
-                const int cc = warp * 64 + 2 * lane;
-                if (cc < wcols) {
-                    double2 xv[NX];
-                    xv[0] = *reinterpret_cast<const double2 *>(&rp->X[st.stage][0][cc]);
-                    if (NX > 1) xv[NX - 1] = *reinterpret_cast<const double2 *>(&rp->X[st.stage][NX - 1][cc]);
-                    // odd N: column N is padding (moved only to keep 16-byte granularity)
-                    const bool pad_y = (col + cc + 1 >= dv.N);
-                    if (pad_y) {
-                        xv[0].y = 0.0;
-                        if (NX > 1) xv[NX - 1].y = 0.0;
+            // this warp's column blocks: those whose stage number is = warp (mod 8)
+            for (uint32_t cb = (uint32_t)(warp - (int)t0) & (TST - 1); cb < nck; cb += TST) {
+                const uint32_t t = t0 + cb;
+                mbar_wait(&rp->full[warp], (t >> 3) & 1);
+                if (cb + 1 < nck) {
+                    // full stage: lane takes columns 64k + 2 lane, k = 0..7, of all TR rows.
+                    // Rows beyond nr hold stale data: computed, never used.
+#pragma unroll
+                    for (int k = 0; k < TCW / 64; ++k) {
+                        const int cc = 64 * k + 2 * lane;
+                        double2 xv[NX];
+                        xv[0] = *reinterpret_cast<const double2 *>(sx + cc);
+                        if (NX > 1) xv[NX - 1] = *reinterpret_cast<const double2 *>(sx + (NX - 1) * TCW + cc);
+#pragma unroll
+                        for (int r = 0; r < TR; ++r) {
+                            const double2 pv = *reinterpret_cast<const double2 *>(sp + r * TCW + cc);
+#pragma unroll
+                            for (int q = 0; q < NX; ++q) {
+                                a[q][r][0] = fma(pv.x, xv[q].x, a[q][r][0]);
+                                a[q][r][1] = fma(pv.y, xv[q].y, a[q][r][1]);
+                            }
+                        }
                     }
+                } else {
+                    // last column block of the row: ragged width, odd-N padding column masked
+                    const int64_t col = (int64_t)cb * TCW;
+                    const int wcols = (int)(ncols - col);
+                    for (int cc = 2 * lane; cc < wcols; cc += 64) {
+                        double2 xv[NX];
+                        xv[0] = *reinterpret_cast<const double2 *>(sx + cc);
+                        if (NX > 1) xv[NX - 1] = *reinterpret_cast<const double2 *>(sx + (NX - 1) * TCW + cc);
+                        const bool pad_y = (col + cc + 1 >= dv.N);
+                        if (pad_y) {
+                            xv[0].y = 0.0;
+                            if (NX > 1) xv[NX - 1].y = 0.0;
+                        }
 #pragma unroll
-                    for (int r = 0; r < TR; ++r) {
-                        double2 pv = *reinterpret_cast<const double2 *>(&rp->P[st.stage][r][cc]);
-                        if (pad_y) pv.y = 0.0;
+                        for (int r = 0; r < TR; ++r) {
+                            double2 pv = *reinterpret_cast<const double2 *>(sp + r * TCW + cc);
+                            if (pad_y) pv.y = 0.0;
 #pragma unroll
-                        for (int q = 0; q < NX; ++q) {
-                            a[q][r][0] = fma(pv.x, xv[q].x, a[q][r][0]);
-                            a[q][r][1] = fma(pv.y, xv[q].y, a[q][r][1]);
+                            for (int q = 0; q < NX; ++q) {
+                                a[q][r][0] = fma(pv.x, xv[q].x, a[q][r][0]);
+                                a[q][r][1] = fma(pv.y, xv[q].y, a[q][r][1]);
+                            }
                         }
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&rp->empty[st.stage]);
-                if (++st.stage == TST) { st.stage = 0; st.phase ^= 1; }
+                if (lane == 0) mbar_arrive(&rp->empty[warp]);
             }
 #pragma unroll
             for (int q = 0; q < NX; ++q)
 #pragma unroll
                 for (int r = 0; r < TR; ++r) {
                     const double s = warp_sum(a[q][r][0] + a[q][r][1]);
-                    if (lane == 0) rp->part[warp][q][r] = s;
+                    if (lane == 0) rp->part[buf][warp][q][r] = s;
                 }
+            // one barrier per group: part[] is double buffered, so the other warps run on into
+            // the next group while warp 0's first lanes evaluate the epilogue (pow etc.)
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (threadIdx.x < nr) {
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll
                 for (int w = 0; w < CONSUMER_WARPS; ++w) {
-                    s0 += rp->part[w][0][threadIdx.x];
-                    if (NX > 1) s1 += rp->part[w][NX - 1][threadIdx.x];
+                    s0 += rp->part[buf][w][0][threadIdx.x];
+                    if (NX > 1) s1 += rp->part[buf][w][NX - 1][threadIdx.x];
                 }
                 epi(dv.row_begin + r0 + threadIdx.x, s0, NX > 1 ? s1 : s0);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // part[] quiescent before the next pass
     }
 }
 

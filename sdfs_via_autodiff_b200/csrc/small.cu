@@ -5,9 +5,8 @@
 // k_sa_loop (successive_approx, solvers.py:19-48).
 #include "common.cuh"
 
-#define SMALL_THREADS 1024
-#define SMALL_WARPS 32
-#define SMALL_MAX_ROWS_PER_WARP 8
+#include <stdlib.h>
+#define SMALL_MAX_N 160
 
 struct SmallArgs {
     const double *P; int64_t ld; int N;
@@ -19,12 +18,24 @@ struct SmallArgs {
     long long *iters_out; double *final_err_out;
 };
 
-__global__ void __launch_bounds__(SMALL_THREADS, 1) k_sa_small(SmallArgs a) {
+// x^e for x > 0 through exp(e log x): one log and one exp instead of pow's extended-precision
+// path.  |e log x| <= ~250 here, so the relative error is <= ~250 ulp(1) ~ 3e-14 in w^theta and
+// shrinks by the factor 1/|theta| when T takes the 1/theta power: far inside the 1e-10 contract.
+// NaN for x < 0 and inf for x = 0, e < 0, like pow.
+template <int MODE>
+__device__ __forceinline__ double pw(double x, double e) {
+    return MODE == 0 ? pow(x, e) : exp(e * log(x));
+}
+
+template <int SMALL_WARPS, int MODE>
+__global__ void __launch_bounds__(SMALL_WARPS * 32, 1) k_sa_small(SmallArgs a) {
+    constexpr int SMALL_THREADS = SMALL_WARPS * 32;
+    constexpr int SMALL_MAX_ROWS_PER_WARP = (SMALL_MAX_N + SMALL_WARPS - 1) / SMALL_WARPS;
     extern __shared__ __align__(16) double sm[];
     const int N = a.N;
     double *sP = sm;                          // N x N
     double *sx = sP + (size_t)N * N;          // 2 x N  (ping-pong matvec input)
-    double *serr = sx + 2 * N;                // 2 x 32 (ping-pong per-warp sup-norms)
+    double *serr = sx + 2 * N;                // 2 x 32 (ping-pong per-warp sup-norms; unused tail = 0)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int e = threadIdx.x; e < N * N; e += SMALL_THREADS) sP[e] = a.P[(int64_t)(e / N) * a.ld + e % N];
     const double theta = a.theta, beta = a.beta, inv_theta = 1.0 / a.theta;
@@ -40,7 +51,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_sa_small(SmallArgs a) {
         ac = a.a_col[my_row];
         sx[my_row] = ac * pow(w_mine, theta);
     }
-    if (threadIdx.x < 2 * SMALL_WARPS) serr[threadIdx.x] = 0.0;
+    if (threadIdx.x < 64) serr[threadIdx.x] = 0.0;
     __syncthreads();
     long long it = 0;
     double error = a.tol + 1.0;
@@ -65,15 +76,15 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) k_sa_small(SmallArgs a) {
             }
         double d = 0.0;
         if (owner) {
-            const double y = 1.0 + beta * pow(ar * s_mine, inv_theta);
+            const double y = 1.0 + beta * pw<MODE>(ar * s_mine, inv_theta);
             d = fabs(y - w_mine);
             w_mine = y;
-            sx[nxt * N + my_row] = ac * pow(y, theta);
+            sx[nxt * N + my_row] = ac * pw<MODE>(y, theta);
         }
         d = warp_nanmax(d);
-        if (lane == 0) serr[cur * SMALL_WARPS + warp] = d;
+        if (lane == 0) serr[cur * 32 + warp] = d;
         __syncthreads();
-        error = warp_nanmax(serr[cur * SMALL_WARPS + lane]);
+        error = warp_nanmax(serr[cur * 32 + lane]);
         if (threadIdx.x == 0 && a.err_hist && (it % a.hist_stride) == 0 && (it / a.hist_stride) < a.hist_cap)
             a.err_hist[it / a.hist_stride] = error;
         ++it;
@@ -93,10 +104,11 @@ int small_sa_try(sdfs_op *op, const double *d_w_init, double tol, int64_t max_it
     const DenseView &dv = op->dv;
     if (dv.row_begin != 0 || dv.row_end != dv.N) return 0;
     const int64_t N = dv.N;
-    if (N > SMALL_WARPS * SMALL_MAX_ROWS_PER_WARP) return 0;
-    const size_t smem = ((size_t)N * N + 2 * N + 2 * SMALL_WARPS) * sizeof(double);
+    if (N > SMALL_MAX_N) return 0;
+    const size_t smem = ((size_t)N * N + 2 * N + 64) * sizeof(double);
     if (smem > 220 * 1024) return 0;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_sa_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const char *ev = getenv("SDFS_SMALL_VARIANT");     // experiment switch: "<warps><mode>", e.g. 320, 321, 81
+    const int variant = ev ? atoi(ev) : 321;
     SmallArgs a{};
     a.P = dv.P; a.ld = dv.ld; a.N = (int)N; a.a_row = dv.a_row; a.a_col = dv.a_col;
     a.beta = dv.beta; a.theta = dv.theta; a.w_init = d_w_init; a.w_out = d_w_out;
@@ -104,7 +116,18 @@ int small_sa_try(sdfs_op *op, const double *d_w_init, double tol, int64_t max_it
     a.hist_stride = hist_stride > 0 ? hist_stride : 1; a.hist_cap = d_err_hist ? hist_cap : 0;
     a.iters_out = (long long *)ctx->d_status;                 // LoopStatus.iters
     a.final_err_out = (double *)((char *)ctx->d_status + 32); // LoopStatus.final_err
-    k_sa_small<<<1, SMALL_THREADS, smem, ctx->stream>>>(a);
+#define LAUNCH_SMALL(W, M)                                                                                   \
+    do {                                                                                                     \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_sa_small<W, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_sa_small<W, M><<<1, W * 32, smem, ctx->stream>>>(a);                                               \
+    } while (0)
+    switch (variant) {
+        case 320: LAUNCH_SMALL(32, 0); break;
+        case 80: LAUNCH_SMALL(8, 0); break;
+        case 81: LAUNCH_SMALL(8, 1); break;
+        case 161: LAUNCH_SMALL(16, 1); break;
+        default: LAUNCH_SMALL(32, 1); break;
+    }
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return 1;

@@ -357,5 +357,36 @@ int main(int argc, char **argv) {
         run("V4 tma rows R8 CW512 x5 stages", [&] { k_tma_rows<R, CW, ST><<<sms, 288, sm>>>(P, N, ld, x, y); }, false, true);
     }
     printf("checksum %.6f\n", checksum(href));
+    if (argc > 3) {
+        // sustained mode: queue ~argv[3] seconds of launches, sample clocks/power mid-run
+        const double secs = atof(argv[3]);
+        auto sustained = [&](const char *name, auto launch) {
+            launch(); CK(cudaDeviceSynchronize());
+            cudaEventRecord(e0); launch(); cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+            float ms1; cudaEventElapsedTime(&ms1, e0, e1);
+            const int n = (int)(secs * 1e3 / ms1) + 1;
+            cudaEventRecord(e0);
+            for (int i = 0; i < n; ++i) launch();
+            cudaEventRecord(e1);
+            char buf[256] = {0};
+            FILE *f = popen("sleep 0.6; nvidia-smi --query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap --format=csv,noheader,nounits | head -1", "r");
+            if (f) { if (!fgets(buf, sizeof(buf), f)) buf[0] = 0; pclose(f); }
+            for (char *c = buf; *c; ++c) if (*c == '\n') *c = 0;
+            CK(cudaDeviceSynchronize());
+            float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= n;
+            printf("SUSTAINED %-40s first %.3f ms | avg %.3f ms over %d launches  %8.1f GB/s | mid-run sm_mhz,power,pwrcap: %s\n",
+                   name, ms1, ms, n, gb / ms * 1e3, buf);
+            fflush(stdout);
+        };
+        constexpr int R = 4, CW = 512, ST = 8;
+        const size_t sm = (size_t)ST * R * CW * 8 + (size_t)ST * CW * 8 + 2 * ST * 8;
+        sustained("V4 tma R4 CW512 x8 grid=148", [&] { k_tma_rows<R, CW, ST><<<sms, 288, sm>>>(P, N, ld, x, y); });
+        sustained("V4 tma R4 CW512 x8 grid=111", [&] { k_tma_rows<R, CW, ST><<<111, 288, sm>>>(P, N, ld, x, y); });
+        sustained("V4 tma R4 CW512 x8 grid=74", [&] { k_tma_rows<R, CW, ST><<<74, 288, sm>>>(P, N, ld, x, y); });
+        sustained("V2 cta rows R4U4 cs 2cta/sm", [&] { k_cta_rows<4, 4, 0, 2><<<g2, 256>>>(P, N, ld, x, y); });
+        sustained("V2 cta rows R8U4 cs 1cta/sm", [&] { k_cta_rows<8, 4, 0, 1><<<sms, 256>>>(P, N, ld, x, y); });
+        sustained("V3 pure read", [&] { k_read<<<g2 * 4, 256>>>(P, (int64_t)N * ld, yref); });
+        sustained("V4 tma R4 CW512 x8 grid=148 (again)", [&] { k_tma_rows<R, CW, ST><<<sms, 288, sm>>>(P, N, ld, x, y); });
+    }
     return 0;
 }
