@@ -98,26 +98,33 @@ __device__ __forceinline__ void dense_pass_tma(const DenseView &dv, const double
     const int64_t my_groups = (ngroups > (int64_t)blockIdx.x) ? (ngroups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     st.t = t_begin + (uint32_t)my_groups * nck;
     if (warp == PRODUCER_WARP) {
-        if (lane == 0) {
-            // order the generic-proxy stores that produced x (before the last grid barrier)
-            // ahead of the async-proxy reads below
-            asm volatile("fence.proxy.async;" ::: "memory");
-            uint32_t t = t_begin;
-            for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-                const int64_t r0 = g * TR;
-                const int nr = (int)(nloc - r0 < TR ? nloc - r0 : TR);
-                const double *p0 = dv.P + r0 * dv.ld;
-                for (uint32_t cb = 0; cb < nck; ++cb, ++t) {
-                    const int64_t col = (int64_t)cb * TCW;
-                    const uint32_t bytes = (uint32_t)((ncols - col < TCW ? ncols - col : TCW) * 8);
-                    const int slot = t & (TST - 1);
+        // Producer warp.  Lane 0 owns the barrier handshake; the per-stage bulk copies are
+        // issued by parallel lanes (lane r < nr: row r of the group, lane TR (+1): the x
+        // chunk(s)) with incrementally advanced pointers, so the serial work per stage is one
+        // try_wait + one expect_tx -- the producer must never be the per-stage latency bound.
+        // Order the generic-proxy stores that produced x (before the last grid barrier) ahead
+        // of the async-proxy reads below.
+        asm volatile("fence.proxy.async;" ::: "memory");
+        uint32_t t = t_begin;
+        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+            const int64_t r0 = g * TR;
+            const int nr = (int)(nloc - r0 < TR ? nloc - r0 : TR);
+            const double *src = nullptr;                     // this lane's source, advanced by TCW per stage
+            int role = -1;                                   // 0 = P row, 1 = x vector
+            if (lane < nr) { src = dv.P + (r0 + lane) * dv.ld; role = 0; }
+            else if (lane == TR) { src = x0; role = 1; }
+            else if (NX > 1 && lane == TR + 1) { src = x1; role = 1; }
+            int64_t left = ncols;                            // columns still to move in this row
+            for (uint32_t cb = 0; cb < nck; ++cb, ++t, left -= TCW, src += TCW) {
+                const uint32_t bytes = (uint32_t)((left < TCW ? left : TCW) * 8);
+                const int slot = t & (TST - 1);
+                if (lane == 0) {
                     mbar_wait(&rp->empty[slot], ((t >> 3) & 1) ^ 1);
                     mbar_expect_tx(&rp->full[slot], bytes * (uint32_t)(nr + NX));
-                    for (int r = 0; r < nr; ++r)
-                        bulk_g2s(&rp->P[slot][r][0], p0 + (int64_t)r * dv.ld + col, bytes, &rp->full[slot]);
-                    bulk_g2s(&rp->X[slot][0][0], x0 + col, bytes, &rp->full[slot]);
-                    if (NX > 1) bulk_g2s(&rp->X[slot][NX - 1][0], x1 + col, bytes, &rp->full[slot]);
                 }
+                __syncwarp();
+                if (role == 0) bulk_g2s(&rp->P[slot][lane][0], src, bytes, &rp->full[slot]);
+                else if (role == 1) bulk_g2s(&rp->X[slot][lane - TR][0], src, bytes, &rp->full[slot]);
             }
         }
     } else {
