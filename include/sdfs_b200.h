@@ -136,6 +136,9 @@ int sdfs_op_apply_T(sdfs_op *op, const double *d_w_in, double *d_w_out);
 int sdfs_op_apply_jvp(sdfs_op *op, const double *d_w, const double *d_v, double *d_out);
 /* plain y = P x (used by tests and the CPU/GPU bandwidth comparison) */
 int sdfs_op_apply_P(sdfs_op *op, const double *d_x, double *d_y);
+/* diagnostic: `reps` back-to-back launches of the dense row-stream pass alone (mode 0 = T
+ * epilogue, 3 = plain P x) on the x staged by the previous apply; average device ms. */
+int sdfs_op_bench_pass(sdfs_op *op, int mode, int reps, double *avg_ms);
 /* SDF from a fixed point (paper/autosdfs.tex:374-384; no reference code):
  * q_f(n) = sum_n' P(n,n') Mbar(n,n'),  euler(n) = beta^theta s(n)/(w(n)-1)^theta - 1.
  * Either output may be NULL. */

@@ -71,6 +71,7 @@ _SIGS = {
     "sdfs_op_apply_T": (C.c_int, [c_vp, c_vp, c_vp]),
     "sdfs_op_apply_jvp": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "sdfs_op_apply_P": (C.c_int, [c_vp, c_vp, c_vp]),
+    "sdfs_op_bench_pass": (C.c_int, [c_vp, C.c_int, C.c_int, P(c_f64)]),
     "sdfs_op_sdf": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "sdfs_op_sdf_rows": (C.c_int, [c_vp, c_vp, P(c_i64), c_i64, c_vp]),
     "sdfs_solve_sa": (C.c_int, [c_vp, c_vp, c_f64, c_i64, c_vp, P(c_i64), P(c_f64), c_vp, c_i64, c_i64]),

@@ -355,6 +355,28 @@ int sdfs_op_apply_P(sdfs_op *op, const double *d_x, double *d_y) {
     return run_apply(op, 3, nullptr, d_x, e, true, false);
 }
 
+// Back-to-back launches of the dense pass alone (no prologue, no allocation, no host work in
+// between): the sustained-rate measurement behind profiles/ and a diagnostic for the bench.
+// mode 0 = T epilogue, 3 = plain P x.  x must have been staged by a previous apply.
+int sdfs_op_bench_pass(sdfs_op *op, int mode, int reps, double *avg_ms) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_bench_pass: NULL op");
+    sdfs_ctx *ctx = op->ctx;
+    ARG_CHECK(ctx, op->storage == SDFS_STORAGE_DENSE && reps >= 1 && avg_ms && (mode == 0 || mode == 3));
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(op_ensure_work(op, 4));
+    double *x0 = op->work, *scratch = op->work + 3 * op->ldv;
+    EpiArgs e{mode, op->dv.a_row, nullptr, nullptr, op->dv.beta, op->dv.theta, scratch, nullptr};
+    TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int i = 0; i < reps; ++i) TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *avg_ms = (double)ms / reps;
+    return SDFS_OK;
+}
+
 int sdfs_op_sdf(sdfs_op *op, const double *d_w, double *d_qf, double *d_euler) {
     if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_sdf: NULL op");
     const bool dense = op->storage == SDFS_STORAGE_DENSE;

@@ -170,6 +170,12 @@ class WCOperator:
         check(lib.sdfs_op_apply_P(self.handle, d.ptr, out.ptr), self.ctx.handle)
         return out
 
+    def bench_pass(self, mode=0, reps=20):
+        """Average device ms of `reps` back-to-back dense passes (diagnostic; see sdfs_b200.h)."""
+        ms = C.c_double()
+        check(lib.sdfs_op_bench_pass(self.handle, int(mode), int(reps), C.byref(ms)), self.ctx.handle)
+        return ms.value
+
     def sdf(self, w):
         """(q_f, euler_residual): one-period risk-free price E[M'|x] and the Euler-equation
         residual β^θ s/(w-1)^θ - 1 of paper/autosdfs.tex:374-384."""
