@@ -1,5 +1,6 @@
 // Shared host/device definitions for libsdfs_b200 (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <stdint.h>
@@ -74,6 +75,7 @@ static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * 
 // Operator description passed by value to kernels.
 // ---------------------------------------------------------------------------
 struct DenseView {
+    CUtensorMap tm;        // 2-D TMA descriptor of the local P slice (box 8 rows x 256 cols); valid iff vec2
     const double *P;       // rows [row_begin,row_end), leading dimension ld
     int64_t N, ld;
     int64_t row_begin, row_end;
@@ -81,7 +83,7 @@ struct DenseView {
     const double *a_col;   // N
     const double *e_sdf;   // N or null
     double beta, theta;
-    int vec2;              // 1 when every row of P is 16-byte aligned
+    int vec2;              // 1 when every row of P is 16-byte aligned (TMA path)
 };
 
 // Factor-structured operator: out = M_D ... M_1 applied mode by mode.

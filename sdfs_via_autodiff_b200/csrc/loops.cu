@@ -274,7 +274,7 @@ struct SAArgs {
 };
 
 template <class Op>
-__global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_sa_loop(Op op, SAArgs a, LoopEnv env) {
+__global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_sa_loop(const __grid_constant__ Op op, SAArgs a, LoopEnv env) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ double smem[SDFS_WARPS * NVAL + NVAL];
@@ -579,7 +579,7 @@ __device__ __forceinline__ bool gmres_device(cg::grid_group &grid, const Op &op,
 }
 
 template <class Op>
-__global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_newton_loop(Op op, NewtonArgs a, LoopEnv env) {
+__global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_newton_loop(const __grid_constant__ Op op, NewtonArgs a, LoopEnv env) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ double smem[SDFS_WARPS * NVAL + NVAL];

@@ -61,7 +61,7 @@ __device__ __forceinline__ void apply_epilogue(const EpiArgs &e, int64_t n, doub
 
 template <int NX>
 __global__ void __launch_bounds__(SDFS_THREADS, 1)
-k_dense_apply(DenseView dv, const double *x0, const double *x1, EpiArgs e) {
+k_dense_apply(const __grid_constant__ DenseView dv, const double *x0, const double *x1, EpiArgs e) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     RowPipe<NX> *rp = reinterpret_cast<RowPipe<NX> *>(dyn_smem);
     PipeState st;
@@ -82,6 +82,38 @@ __global__ void k_kron_last(KronView kv, int m, const double *__restrict__ in, c
                        if (s0_done) apply_epilogue(e, idx, s0_done[idx], s);
                        else apply_epilogue(e, idx, s, s);
                    });
+}
+
+// 2-D TMA descriptor of the local row slice of P: dims (N columns, nloc rows), row pitch ld,
+// box 256 columns x 8 rows, zero fill outside the matrix.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int dense_view_finalize(sdfs_ctx *ctx, DenseView *dv) {
+    const int64_t nloc = dv->row_end - dv->row_begin;
+    dv->vec2 = ((dv->ld % 2) == 0 && ((uintptr_t)dv->P % 16) == 0 && nloc > 0) ? 1 : 0;
+    memset(&dv->tm, 0, sizeof(dv->tm));
+    if (!dv->vec2) return SDFS_OK;
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn) return sdfs_set_error(ctx, SDFS_ERR_UNSUPPORTED, "driver lacks cuTensorMapEncodeTiled");
+        encode = (EncodeTiledFn)fn;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)dv->N, (cuuint64_t)nloc};
+    cuuint64_t strides[1] = {(cuuint64_t)dv->ld * 8};
+    cuuint32_t box[2] = {TCW, TR};
+    cuuint32_t es[2] = {1, 1};
+    const CUresult r = encode(&dv->tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)dv->P, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        dv->vec2 = 0;      // e.g. a pitch the TMA unit cannot address: use the direct-load path
+        memset(&dv->tm, 0, sizeof(dv->tm));
+    }
+    return SDFS_OK;
 }
 
 int op_ensure_work(sdfs_op *op, int n_vectors) {
@@ -198,7 +230,10 @@ int sdfs_op_from_dense(sdfs_ctx *ctx, const double *d_P, int64_t N, int64_t ld, 
     op->dv.row_begin = row_begin; op->dv.row_end = row_end;
     op->dv.a_row = d_a_row; op->dv.a_col = d_a_col; op->dv.e_sdf = nullptr;
     op->dv.beta = beta; op->dv.theta = theta;
-    op->dv.vec2 = ((ld % 2) == 0 && ((uintptr_t)d_P % 16) == 0) ? 1 : 0;
+    {
+        const int rc = dense_view_finalize(ctx, &op->dv);
+        if (rc) { delete op; return rc; }
+    }
     *out = op;
     return SDFS_OK;
 }
@@ -254,7 +289,9 @@ int sdfs_op_from_factors(sdfs_ctx *ctx, sdfs_factors *f, int storage, sdfs_op **
         op->dv.P = op->own_P; op->dv.N = N; op->dv.ld = ld;
         op->dv.row_begin = rb; op->dv.row_end = re;
         op->dv.a_row = op->own_a_row; op->dv.a_col = op->own_a_col; op->dv.e_sdf = op->own_e_sdf;
-        op->dv.beta = beta; op->dv.theta = theta; op->dv.vec2 = 1;
+        op->dv.beta = beta; op->dv.theta = theta;
+        rc = dense_view_finalize(ctx, &op->dv);
+        if (rc) { sdfs_op_destroy(op); return rc; }
     }
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {

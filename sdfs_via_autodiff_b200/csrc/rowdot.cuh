@@ -2,12 +2,12 @@
 // application  (s = P x with fused prologue/epilogue).
 //
 // Primary path (rows 16-byte aligned): TMA-fed CTA-cooperative rows.
-//   A CTA owns groups of TR = 4 consecutive rows (group g -> CTA g mod grid, so the
+//   A CTA owns groups of TR = 8 consecutive rows (group g -> CTA g mod grid, so the
 //   whole grid sweeps one compact window of P).  One producer thread streams each
-//   group as [TR rows x TCW = 512 columns] stages with cp.async.bulk (TMA bulk copy,
-//   4 KB contiguous per row) plus the matching 4 KB chunk of x into a TST = 8 deep
-//   shared-memory ring guarded by full/empty mbarriers (128 KB of P in flight per
-//   SM).  Ring slot w belongs to consumer warp w, which contracts the whole stage
+//   group as [8 rows x 256 columns] boxes with ONE cp.async.bulk.tensor.2d (TMA
+//   tensor copy, 16 KB) plus one bulk copy of the matching 2 KB chunk of x per stage
+//   into a TST = 8 deep shared-memory ring guarded by full/empty mbarriers (128 KB
+//   of P in flight per SM).  Ring slot w belongs to consumer warp w, which contracts the whole stage
 //   (conflict-free 16-byte LDS), accumulates per-lane partials in a fixed column
 //   order, and the warps' row partials are combined in a fixed order per row group.
 //   The TMA ring measured 7.41 TB/s on an 88 GB P (profiles/r01_bw_probe.md), ahead
@@ -19,8 +19,8 @@
 #pragma once
 #include "common.cuh"
 
-#define TR 4          // rows per group
-#define TCW 512       // columns per stage
+#define TR 8          // rows per group = rows of one TMA box
+#define TCW 256       // columns per stage = columns of one TMA box (hardware limit 256)
 #define TST 8         // stages in the ring
 #define CONSUMER_WARPS 8
 #define PRODUCER_WARP 8
@@ -46,20 +46,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// 1-D bulk copy (x chunk) and 2-D tensor copy (P box), both completing on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_2d_g2s(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
 // Shared-memory ring.  NX = number of x vectors contracted in the same P stream.
 // Ring slot w belongs to consumer warp w: the producer fills slots round-robin, warp w
 // consumes every 8th stage on its own, so a warp has 8 stage-times to turn one stage
-// around (the ring keeps feeding HBM at full rate even when the SM clock drops under the
-// power cap) and a stage is released by a single arrive.
+// around and a stage is released by a single arrive.
 template <int NX>
 struct RowPipe {
-    double P[TST][TR][TCW];          // 128 KB
-    double X[TST][NX][TCW];          // 32 KB per x vector
+    double P[TST][TR][TCW];          // 128 KB: one 8 x 256 TMA box per slot
+    double X[TST][NX][TCW];          // 16 KB per x vector
     double part[2][CONSUMER_WARPS][NX][TR];   // per-warp row partials, double buffered by group
     uint64_t full[TST], empty[TST];
 };
@@ -82,49 +86,43 @@ __device__ __forceinline__ void pipe_init(RowPipe<NX> *rp, PipeState &st) {
 }
 
 // One pass over this rank's rows with the TMA ring.  Block = 9 warps (8 consumers +
-// 1 producer).  epi(n_global, s0, s1) runs on thread r (< rows in group) of warp 0.
-// Preconditions: dv.vec2 (16-byte aligned rows, ld even), x0/x1 16-byte aligned and
-// readable up to index round_up(N, 2).
+// 1 producer).  Per stage the producer issues ONE 2-D tensor copy (8 rows x 256 columns of
+// P = 16 KB; rows/columns outside the matrix are zero-filled by the TMA unit, so ragged
+// edges and odd N need no special cases) and ONE bulk copy of the matching 2 KB of x.
+// epi(n_global, s0, s1) runs on thread r (< rows in group) of warp 0.
+// Preconditions: dv.vec2 (dv.tm valid), x0/x1 16-byte aligned, readable and finite up to
+// index round_up(N, 2).  `dv` must live in kernel parameter space (__grid_constant__).
 template <int NX, class Epi>
 __device__ __forceinline__ void dense_pass_tma(const DenseView &dv, const double *x0, const double *x1,
                                                RowPipe<NX> *rp, PipeState &st, Epi &&epi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nloc = dv.row_end - dv.row_begin;
     const int64_t ngroups = (nloc + TR - 1) / TR;
-    const int64_t ncols = (dv.N + 1) & ~(int64_t)1;          // even number of columns to move (ld >= ncols)
-    const uint32_t nck = (uint32_t)((ncols + TCW - 1) / TCW);
+    const int64_t ncols = (dv.N + 1) & ~(int64_t)1;          // x columns to move (even count)
+    const uint32_t nck = (uint32_t)((dv.N + TCW - 1) / TCW);
     const uint32_t t_begin = st.t;
     // every thread advances the shared stage counter identically
     const int64_t my_groups = (ngroups > (int64_t)blockIdx.x) ? (ngroups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     st.t = t_begin + (uint32_t)my_groups * nck;
     if (warp == PRODUCER_WARP) {
-        // Producer warp.  Lane 0 owns the barrier handshake; the per-stage bulk copies are
-        // issued by parallel lanes (lane r < nr: row r of the group, lane TR (+1): the x
-        // chunk(s)) with incrementally advanced pointers, so the serial work per stage is one
-        // try_wait + one expect_tx -- the producer must never be the per-stage latency bound.
-        // Order the generic-proxy stores that produced x (before the last grid barrier) ahead
-        // of the async-proxy reads below.
-        asm volatile("fence.proxy.async;" ::: "memory");
-        uint32_t t = t_begin;
-        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-            const int64_t r0 = g * TR;
-            const int nr = (int)(nloc - r0 < TR ? nloc - r0 : TR);
-            const double *src = nullptr;                     // this lane's source, advanced by TCW per stage
-            int role = -1;                                   // 0 = P row, 1 = x vector
-            if (lane < nr) { src = dv.P + (r0 + lane) * dv.ld; role = 0; }
-            else if (lane == TR) { src = x0; role = 1; }
-            else if (NX > 1 && lane == TR + 1) { src = x1; role = 1; }
-            int64_t left = ncols;                            // columns still to move in this row
-            for (uint32_t cb = 0; cb < nck; ++cb, ++t, left -= TCW, src += TCW) {
-                const uint32_t bytes = (uint32_t)((left < TCW ? left : TCW) * 8);
-                const int slot = t & (TST - 1);
-                if (lane == 0) {
+        if (lane == 0) {
+            // order the generic-proxy stores that produced x (before the last grid barrier)
+            // ahead of the async-proxy reads below
+            asm volatile("fence.proxy.async;" ::: "memory");
+            uint32_t t = t_begin;
+            for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+                const int row0 = (int)(g * TR);
+                for (uint32_t cb = 0; cb < nck; ++cb, ++t) {
+                    const int col = (int)(cb * TCW);
+                    const int64_t left = ncols - col;
+                    const uint32_t xbytes = (uint32_t)((left < TCW ? left : TCW) * 8);
+                    const int slot = t & (TST - 1);
                     mbar_wait(&rp->empty[slot], ((t >> 3) & 1) ^ 1);
-                    mbar_expect_tx(&rp->full[slot], bytes * (uint32_t)(nr + NX));
+                    mbar_expect_tx(&rp->full[slot], (uint32_t)(TR * TCW * 8) + (uint32_t)NX * xbytes);
+                    tma_2d_g2s(&rp->P[slot][0][0], &dv.tm, col, row0, &rp->full[slot]);
+                    bulk_g2s(&rp->X[slot][0][0], x0 + col, xbytes, &rp->full[slot]);
+                    if (NX > 1) bulk_g2s(&rp->X[slot][NX - 1][0], x1 + col, xbytes, &rp->full[slot]);
                 }
-                __syncwarp();
-                if (role == 0) bulk_g2s(&rp->P[slot][lane][0], src, bytes, &rp->full[slot]);
-                else if (role == 1) bulk_g2s(&rp->X[slot][lane - TR][0], src, bytes, &rp->full[slot]);
             }
         }
     } else {
@@ -143,48 +141,29 @@ __device__ __forceinline__ void dense_pass_tma(const DenseView &dv, const double
             // this warp's column blocks: those whose stage number is = warp (mod 8)
             for (uint32_t cb = (uint32_t)(warp - (int)t0) & (TST - 1); cb < nck; cb += TST) {
                 const uint32_t t = t0 + cb;
+                const bool last = (cb + 1 == nck);
                 mbar_wait(&rp->full[warp], (t >> 3) & 1);
-                if (cb + 1 < nck) {
-                    // full stage: lane takes columns 64k + 2 lane, k = 0..7, of all TR rows.
-                    // Rows beyond nr hold stale data: computed, never used.
+                // lane takes columns 64k + 2 lane, k = 0..3, of all TR rows (conflict-free LDS.128)
 #pragma unroll
-                    for (int k = 0; k < TCW / 64; ++k) {
-                        const int cc = 64 * k + 2 * lane;
-                        double2 xv[NX];
-                        xv[0] = *reinterpret_cast<const double2 *>(sx + cc);
-                        if (NX > 1) xv[NX - 1] = *reinterpret_cast<const double2 *>(sx + (NX - 1) * TCW + cc);
-#pragma unroll
-                        for (int r = 0; r < TR; ++r) {
-                            const double2 pv = *reinterpret_cast<const double2 *>(sp + r * TCW + cc);
-#pragma unroll
-                            for (int q = 0; q < NX; ++q) {
-                                a[q][r][0] = fma(pv.x, xv[q].x, a[q][r][0]);
-                                a[q][r][1] = fma(pv.y, xv[q].y, a[q][r][1]);
-                            }
-                        }
+                for (int k = 0; k < TCW / 64; ++k) {
+                    const int cc = 64 * k + 2 * lane;
+                    double2 xv[NX];
+                    xv[0] = *reinterpret_cast<const double2 *>(sx + cc);
+                    if (NX > 1) xv[NX - 1] = *reinterpret_cast<const double2 *>(sx + (NX - 1) * TCW + cc);
+                    if (last) {
+                        // beyond N the P box is zero-filled by the TMA unit, but the x slot keeps
+                        // stale shared memory there: mask it (0 * garbage must stay 0)
+                        const int64_t gc = (int64_t)cb * TCW + cc;
+                        if (gc >= dv.N) { xv[0].x = 0.0; if (NX > 1) xv[NX - 1].x = 0.0; }
+                        if (gc + 1 >= dv.N) { xv[0].y = 0.0; if (NX > 1) xv[NX - 1].y = 0.0; }
                     }
-                } else {
-                    // last column block of the row: ragged width, odd-N padding column masked
-                    const int64_t col = (int64_t)cb * TCW;
-                    const int wcols = (int)(ncols - col);
-                    for (int cc = 2 * lane; cc < wcols; cc += 64) {
-                        double2 xv[NX];
-                        xv[0] = *reinterpret_cast<const double2 *>(sx + cc);
-                        if (NX > 1) xv[NX - 1] = *reinterpret_cast<const double2 *>(sx + (NX - 1) * TCW + cc);
-                        const bool pad_y = (col + cc + 1 >= dv.N);
-                        if (pad_y) {
-                            xv[0].y = 0.0;
-                            if (NX > 1) xv[NX - 1].y = 0.0;
-                        }
 #pragma unroll
-                        for (int r = 0; r < TR; ++r) {
-                            double2 pv = *reinterpret_cast<const double2 *>(sp + r * TCW + cc);
-                            if (pad_y) pv.y = 0.0;
+                    for (int r = 0; r < TR; ++r) {
+                        const double2 pv = *reinterpret_cast<const double2 *>(sp + r * TCW + cc);
 #pragma unroll
-                            for (int q = 0; q < NX; ++q) {
-                                a[q][r][0] = fma(pv.x, xv[q].x, a[q][r][0]);
-                                a[q][r][1] = fma(pv.y, xv[q].y, a[q][r][1]);
-                            }
+                        for (int q = 0; q < NX; ++q) {
+                            a[q][r][0] = fma(pv.x, xv[q].x, a[q][r][0]);
+                            a[q][r][1] = fma(pv.y, xv[q].y, a[q][r][1]);
                         }
                     }
                 }

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <math.h>
 #include <vector>
+#include <cuda.h>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
@@ -288,6 +289,117 @@ __global__ void __launch_bounds__(288, 1) k_tma_rows(const double *P, int64_t N,
     }
 }
 
+// ---- V5: 2-D tensor-map TMA, one box per stage, ring slot w owned by consumer warp w --------
+__device__ __forceinline__ void tma_2d_g2s(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// stage = BR rows x BC cols (BC <= 256), NBOX boxes side by side along the columns
+template <int BR, int BC, int NBOX>
+__global__ void __launch_bounds__(288, 1) k_tma2d_rows(const __grid_constant__ CUtensorMap tm, int64_t N, int64_t ld,
+                                                       const double *x, double *y) {
+    constexpr int CW = BC * NBOX;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sP = reinterpret_cast<double *>(smem_raw);                 // [8][NBOX][BR][BC]
+    double *sX = sP + (size_t)8 * BR * CW;                             // [8][CW]
+    uint64_t *full = reinterpret_cast<uint64_t *>(sX + (size_t)8 * CW);
+    uint64_t *empty = full + 8;
+    __shared__ double part[2][8][BR];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 8; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t ngroups = (N + BR - 1) / BR;
+    const uint32_t nck = (uint32_t)((N + CW - 1) / CW);
+    if (warp == 8) {
+        if (lane == 0) {
+            uint32_t t = 0;
+            for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+                const int row0 = (int)(g * BR);
+                for (uint32_t cb = 0; cb < nck; ++cb, ++t) {
+                    const int slot = t & 7;
+                    const int col = (int)(cb * CW);
+                    const int64_t left = ld - col;
+                    const uint32_t xbytes = (uint32_t)((left < CW ? left : CW) * 8);
+                    mbar_wait(&empty[slot], ((t >> 3) & 1) ^ 1);
+                    mbar_expect_tx(&full[slot], (uint32_t)(BR * CW * 8) + xbytes);
+#pragma unroll
+                    for (int b = 0; b < NBOX; ++b)
+                        tma_2d_g2s(sP + ((size_t)slot * NBOX + b) * BR * BC, &tm, col + b * BC, row0, &full[slot]);
+                    bulk_g2s(sX + (size_t)slot * CW, x + col, xbytes, &full[slot]);
+                }
+            }
+        }
+    } else {
+        uint32_t t0 = 0;
+        int buf = 0;
+        const double *sp = sP + (size_t)warp * BR * CW;
+        const double *sx = sX + (size_t)warp * CW;
+        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x, t0 += nck, buf ^= 1) {
+            double a[BR][2];
+#pragma unroll
+            for (int r = 0; r < BR; ++r) a[r][0] = a[r][1] = 0.0;
+            for (uint32_t cb = (uint32_t)(warp - (int)t0) & 7; cb < nck; cb += 8) {
+                const uint32_t t = t0 + cb;
+                mbar_wait(&full[warp], (t >> 3) & 1);
+#pragma unroll
+                for (int b = 0; b < NBOX; ++b)
+#pragma unroll
+                    for (int k = 0; k < BC / 64; ++k) {
+                        const int cc = 64 * k + 2 * lane;
+                        double2 xv = *reinterpret_cast<const double2 *>(sx + b * BC + cc);
+                        if (cb + 1 == nck) {   // x beyond N is not zero-filled by the bulk copy: P is (tensor OOB)
+                            const int64_t gc = (int64_t)cb * CW + b * BC + cc;
+                            if (gc >= N) xv.x = 0.0;
+                            if (gc + 1 >= N) xv.y = 0.0;
+                        }
+#pragma unroll
+                        for (int r = 0; r < BR; ++r) {
+                            const double2 pv = *reinterpret_cast<const double2 *>(sp + ((size_t)b * BR + r) * BC + cc);
+                            a[r][0] = fma(pv.x, xv.x, a[r][0]);
+                            a[r][1] = fma(pv.y, xv.y, a[r][1]);
+                        }
+                    }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[warp]);
+            }
+#pragma unroll
+            for (int r = 0; r < BR; ++r) {
+                const double s = warp_sum(a[r][0] + a[r][1]);
+                if (lane == 0) part[buf][warp][r] = s;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x < BR && g * BR + threadIdx.x < N) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s += part[buf][w][threadIdx.x];
+                y[g * BR + threadIdx.x] = s;
+            }
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static CUtensorMap make_map(const double *P, int64_t N, int64_t nrows, int64_t ld, int bc, int br, CUtensorMapL2promotion prom) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    CUtensorMap tm;
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)nrows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {(cuuint32_t)bc, (cuuint32_t)br};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = ((EncodeTiledFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)P, dims, strides, box, es,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, prom,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed: %d\n", (int)r); exit(4); }
+    return tm;
+}
+
 static double checksum(const std::vector<double> &v) { double s = 0; for (double x : v) s += x * 1e-6; return s; }
 
 int main(int argc, char **argv) {
@@ -356,6 +468,18 @@ int main(int argc, char **argv) {
         CK(cudaFuncSetAttribute(k_tma_rows<R, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         run("V4 tma rows R8 CW512 x5 stages", [&] { k_tma_rows<R, CW, ST><<<sms, 288, sm>>>(P, N, ld, x, y); }, false, true);
     }
+    {
+        CUtensorMap tm = make_map(P, N, N, ld, 256, 8, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        const size_t sm = (size_t)8 * 8 * 256 * 8 + (size_t)8 * 256 * 8 + 128;
+        CK(cudaFuncSetAttribute(k_tma2d_rows<8, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        run("V5 tma2d box 8x256, slot/warp", [&] { k_tma2d_rows<8, 256, 1><<<sms, 288, sm>>>(tm, N, ld, x, y); }, false, true);
+        CUtensorMap tm2 = make_map(P, N, N, ld, 256, 4, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        const size_t sm2 = (size_t)8 * 4 * 512 * 8 + (size_t)8 * 512 * 8 + 128;
+        CK(cudaFuncSetAttribute(k_tma2d_rows<4, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        run("V6 tma2d 2 boxes 4x256, slot/warp", [&] { k_tma2d_rows<4, 256, 2><<<sms, 288, sm2>>>(tm2, N, ld, x, y); }, false, true);
+        CUtensorMap tm3 = make_map(P, N, N, ld, 256, 8, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+        run("V5 tma2d box 8x256, no L2 promotion", [&] { k_tma2d_rows<8, 256, 1><<<sms, 288, sm>>>(tm3, N, ld, x, y); }, false, true);
+    }
     printf("checksum %.6f\n", checksum(href));
     if (argc > 3) {
         // sustained mode: queue ~argv[3] seconds of launches, sample clocks/power mid-run
@@ -381,6 +505,14 @@ int main(int argc, char **argv) {
         constexpr int R = 4, CW = 512, ST = 8;
         const size_t sm = (size_t)ST * R * CW * 8 + (size_t)ST * CW * 8 + 2 * ST * 8;
         sustained("V4 tma R4 CW512 x8 grid=148", [&] { k_tma_rows<R, CW, ST><<<sms, 288, sm>>>(P, N, ld, x, y); });
+        {
+            CUtensorMap tm = make_map(P, N, N, ld, 256, 8, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+            const size_t sm5 = (size_t)8 * 8 * 256 * 8 + (size_t)8 * 256 * 8 + 128;
+            sustained("V5 tma2d box 8x256, slot/warp", [&] { k_tma2d_rows<8, 256, 1><<<sms, 288, sm5>>>(tm, N, ld, x, y); });
+            CUtensorMap tm2 = make_map(P, N, N, ld, 256, 4, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+            const size_t sm6 = (size_t)8 * 4 * 512 * 8 + (size_t)8 * 512 * 8 + 128;
+            sustained("V6 tma2d 2 boxes 4x256, slot/warp", [&] { k_tma2d_rows<4, 256, 2><<<sms, 288, sm6>>>(tm2, N, ld, x, y); });
+        }
         sustained("V4 tma R4 CW512 x8 grid=111", [&] { k_tma_rows<R, CW, ST><<<111, 288, sm>>>(P, N, ld, x, y); });
         sustained("V4 tma R4 CW512 x8 grid=74", [&] { k_tma_rows<R, CW, ST><<<74, 288, sm>>>(P, N, ld, x, y); });
         sustained("V2 cta rows R4U4 cs 2cta/sm", [&] { k_cta_rows<4, 4, 0, 2><<<g2, 256>>>(P, N, ld, x, y); });

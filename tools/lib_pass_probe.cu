@@ -17,7 +17,7 @@ __global__ void k_fillx(double *x, int64_t N, int64_t ld) {
         x[j] = (j < N) ? 1.0 + (double)(j % 13) : 0.0;
 }
 template <int VARIANT>
-__global__ void __launch_bounds__(SDFS_THREADS, 1) k_lib_pass(DenseView dv, const double *x, double *y) {
+__global__ void __launch_bounds__(SDFS_THREADS, 1) k_lib_pass(const __grid_constant__ DenseView dv, const double *x, double *y) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     RowPipe<1> *rp = reinterpret_cast<RowPipe<1> *>(dyn_smem);
     PipeState st;
@@ -38,6 +38,19 @@ int main(int argc, char **argv) {
     CK(cudaDeviceSynchronize());
     DenseView dv{};
     dv.P = P; dv.N = N; dv.ld = ld; dv.row_begin = 0; dv.row_end = N; dv.vec2 = 1;
+    {
+        typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                          const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                          CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr; cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)N}; cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+        cuuint32_t box[2] = {TCW, TR}; cuuint32_t es[2] = {1, 1};
+        if (((EncodeTiledFn)fn)(&dv.tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, P, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            printf("tensor map failed\n"); return 3;
+        }
+    }
     CK(cudaFuncSetAttribute(k_lib_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowPipe<1>)));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const double gb = ((double)N * N * 8 + 2.0 * N * 8) / 1e9;
