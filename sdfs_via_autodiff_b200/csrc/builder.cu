@@ -327,43 +327,61 @@ __global__ void k_build_scalings(int model, KronView kv, const double *__restric
 }
 
 // Dense expansion: P[n, n'] = prod_m M_m[mat_m(n)][i_m(n)][i_m(n')] for local rows.
-// One CTA per row; the D factor-matrix rows are staged in shared memory.
-__global__ void k_expand_dense(KronView kv, int64_t row_begin, int64_t row_end, int64_t ld,
-                               double *__restrict__ P) {
-    extern __shared__ double srow[];           // concatenated factor rows
-    __shared__ int soff[SDFS_MAX_DIMS + 1];
+// One CTA per row.  The column multi-index is split into a leading part (axes 0..h-1, A
+// combinations) and a trailing part (axes h..D-1, B combinations, A*B = N); the partial
+// products over each part are tabulated in shared memory once per row, so every element of
+// the row costs one multiply and the kernel runs at the HBM write rate instead of being
+// bound by 2 D integer divisions per element.
+__global__ void __launch_bounds__(256) k_expand_dense(KronView kv, int64_t row_begin, int64_t row_end, int64_t ld,
+                                                      int h, int A, int B, double *__restrict__ P) {
+    extern __shared__ double sh[];
+    double *srow = sh;                         // concatenated factor rows of this P row
+    __shared__ int soff[SDFS_MAX_DIMS];        // offset of the factor row of axis d in srow
+    int nsum = 0;
+    for (int d = 0; d < kv.D; ++d) nsum += kv.shape[d];
+    double *Ta = sh + nsum, *Tb = Ta + A;
     for (int64_t row = row_begin + blockIdx.x; row < row_end; row += gridDim.x) {
         __syncthreads();
         int c[SDFS_MAX_DIMS];
         int64_t rem = row;
         for (int d = kv.D - 1; d >= 0; --d) { c[d] = (int)(rem % kv.shape[d]); rem /= kv.shape[d]; }
         int off = 0;
-        for (int m = 0; m < kv.n_modes; ++m) {
+        for (int d = 0; d < kv.D; ++d) {
+            // the mode that contracts axis d
+            int m = 0;
+            for (int mm = 0; mm < kv.n_modes; ++mm) if (kv.modes[mm].dim == d) m = mm;
             const KronMode &md = kv.modes[m];
-            const int n = kv.shape[md.dim];
+            const int n = kv.shape[d];
             int mat = 0;
-            for (int d = 0; d < kv.D; ++d) mat += c[d] * md.mstride[d];
-            const double *src = md.mat + ((int64_t)mat * n + c[md.dim]) * n;
+            for (int dd = 0; dd < kv.D; ++dd) mat += c[dd] * md.mstride[dd];
+            const double *src = md.mat + ((int64_t)mat * n + c[d]) * n;
             for (int j = threadIdx.x; j < n; j += blockDim.x) srow[off + j] = src[j];
-            if (threadIdx.x == 0) soff[m] = off;
+            if (threadIdx.x == 0) soff[d] = off;
             off += n;
         }
         __syncthreads();
+        for (int e = threadIdx.x; e < A + B; e += blockDim.x) {
+            const bool lead = e < A;
+            int r2 = lead ? e : e - A;
+            double v = 1.0;
+            // multiply in increasing-axis order within each part
+            const int d0 = lead ? 0 : h, d1 = lead ? h : kv.D;
+            int cc[SDFS_MAX_DIMS];
+            for (int d = d1 - 1; d >= d0; --d) { cc[d] = r2 % kv.shape[d]; r2 /= kv.shape[d]; }
+            for (int d = d0; d < d1; ++d) v *= srow[soff[d] + cc[d]];
+            if (lead) Ta[e] = v; else Tb[e - A] = v;
+        }
+        __syncthreads();
         double *dst = P + (row - row_begin) * ld;
-        for (int64_t col = threadIdx.x; col < ld; col += blockDim.x) {
-            double v = 0.0;
+        // two columns per thread and step (16-byte stores); ld is even and >= N
+        for (int64_t col = 2 * (int64_t)threadIdx.x; col < ld; col += 2 * blockDim.x) {
+            double2 v = make_double2(0.0, 0.0);
             if (col < kv.N) {
-                int cc[SDFS_MAX_DIMS];
-                int64_t r2 = col;
-                for (int d = kv.D - 1; d >= 0; --d) { cc[d] = (int)(r2 % kv.shape[d]); r2 /= kv.shape[d]; }
-                // multiply in the dense oracle's association order: axis 0 first
-                v = 1.0;
-                for (int d = 0; d < kv.D; ++d) {
-                    for (int m = 0; m < kv.n_modes; ++m)
-                        if (kv.modes[m].dim == d) v *= srow[soff[m] + cc[d]];
-                }
+                const int ia = (int)(col / B), ib = (int)(col - (int64_t)ia * B);
+                v.x = Ta[ia] * Tb[ib];
+                if (col + 1 < kv.N) v.y = (ib + 1 < B) ? Ta[ia] * Tb[ib + 1] : Ta[ia + 1] * Tb[0];
             }
-            dst[col] = v;
+            *reinterpret_cast<double2 *>(dst + col) = v;
         }
     }
 }
@@ -381,12 +399,29 @@ int launch_build_scalings(sdfs_ctx *ctx, const sdfs_factors *f, const KronView &
 }
 
 int launch_expand_dense(sdfs_ctx *ctx, const KronView &kv, int64_t row_begin, int64_t row_end, int64_t ld, double *P) {
-    int smem = 0;
-    for (int m = 0; m < kv.n_modes; ++m) smem += kv.shape[kv.modes[m].dim];
+    int nsum = 0;
+    for (int d = 0; d < kv.D; ++d) nsum += kv.shape[d];
+    // split point: leading part as close to sqrt(N) as possible
+    int h = 1, best_h = 1;
+    double best = 1e300;
+    for (h = 1; h < kv.D; ++h) {
+        double a = 1, b = 1;
+        for (int d = 0; d < h; ++d) a *= kv.shape[d];
+        for (int d = h; d < kv.D; ++d) b *= kv.shape[d];
+        if (a + b < best) { best = a + b; best_h = h; }
+    }
+    h = best_h;
+    int64_t A = 1, B = 1;
+    for (int d = 0; d < h; ++d) A *= kv.shape[d];
+    for (int d = h; d < kv.D; ++d) B *= kv.shape[d];
+    const size_t smem = (size_t)(nsum + A + B) * sizeof(double);
+    if (smem > 200 * 1024)
+        return sdfs_set_error(ctx, SDFS_ERR_UNSUPPORTED, "dense expansion tables need %zu bytes of shared memory", smem);
     const int64_t rows = row_end - row_begin;
     const int grid = (int)(rows < (int64_t)ctx->sm_count * 8 ? rows : (int64_t)ctx->sm_count * 8);
     if (grid <= 0) return SDFS_OK;
-    k_expand_dense<<<grid, 256, smem * sizeof(double), ctx->stream>>>(kv, row_begin, row_end, ld, P);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_expand_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_expand_dense<<<grid, 256, smem, ctx->stream>>>(kv, row_begin, row_end, ld, h, (int)A, (int)B, P);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return SDFS_OK;

@@ -259,8 +259,14 @@ static int sweep_step(sdfs_op *op, SweepWork &w, int64_t B, const double *Win, d
     const int tiles_m = (int)((N + GM - 1) / GM), tiles_b = (int)((B + GN - 1) / GN);
     const size_t smem = (size_t)GSTAGES * (GM + GN) * GS * sizeof(double);
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
+    if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
     k_sweep_gemm<<<tiles_m * tiles_b, GTHREADS, smem, ctx->stream>>>(op->dv.P, N, op->dv.ld, w.V, B, w.ldw, w.sc, w.mz, Win,
                                                                      Wout, sc, track ? w.err_bits : nullptr, tiles_b);
+    if (prof) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
+        ctx->prof_used += 2;
+    }
     ctx->launches += 2;
     CUDA_TRY(ctx, cudaGetLastError());
     return SDFS_OK;

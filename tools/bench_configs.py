@@ -151,7 +151,13 @@ if "c5" in which:
             Wn = S.sweep_apply_T(op, prefs, W)
         ctx.sync()
         dt = (time.perf_counter() - t0) / reps
-        r[f"apply_B{B}"] = dict(ms_with_setup=dt * 1e3, tflops_with_setup=2.0 * N * N * B / dt / 1e12)
+        ctx.prof_enable(8)
+        for _ in range(5):
+            S.sweep_apply_T(op, prefs, W)
+        gms, gn = ctx.prof_read()
+        ctx.prof_enable(0)
+        r[f"apply_B{B}"] = dict(ms_with_setup=dt * 1e3, tflops_with_setup=2.0 * N * N * B / dt / 1e12,
+                                gemm_kernel_ms=gms / gn, gemm_tflops=2.0 * N * N * B / (gms / gn) / 1e9)
     # a solve over a 64-column sub-lattice (the 8 corners + interior points)
     idx = np.linspace(0, 4095, 64).astype(int)
     prefs = lattice[idx]
