@@ -298,6 +298,26 @@ int factors_to_kron(const sdfs_factors *f, KronView *kv) {
         kv->modes[5].mat = f->d_arr[1];  kv->modes[5].dim = 0;                 // z: z_Q[i_zpi,i_hz,i_hzpi]
         kv->modes[5].mstride[1] = nhz * nhzp; kv->modes[5].mstride[2] = nhzp; kv->modes[5].mstride[4] = 1;
     }
+    // fibre-kernel work decomposition per mode
+    long long estride[SDFS_MAX_DIMS];
+    estride[kv->D - 1] = 1;
+    for (int d = kv->D - 2; d >= 0; --d) estride[d] = estride[d + 1] * kv->shape[d + 1];
+    for (int m = 0; m < kv->n_modes; ++m) {
+        KronMode &md = kv->modes[m];
+        md.stride = estride[md.dim];
+        md.nF = md.nM = 0;
+        md.Fcount = md.Mcount = 1;
+        for (int d = 0; d < kv->D; ++d) {
+            if (d == md.dim) continue;
+            if (md.mstride[d] != 0) {
+                md.Mshape[md.nM] = kv->shape[d]; md.Mstride[md.nM] = estride[d]; md.Mmat[md.nM] = md.mstride[d];
+                md.Mcount *= kv->shape[d]; md.nM++;
+            } else {
+                md.Fshape[md.nF] = kv->shape[d]; md.Fstride[md.nF] = estride[d];
+                md.Fcount *= kv->shape[d]; md.nF++;
+            }
+        }
+    }
     return SDFS_OK;
 }
 

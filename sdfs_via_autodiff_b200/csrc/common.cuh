@@ -92,6 +92,13 @@ struct KronMode {
     const double *mat;     // [n_mats][n][n] row = current index, col = next index
     int dim;               // tensor axis contracted by this mode
     int mstride[SDFS_MAX_DIMS];  // matrix id = sum_d coord_d * mstride[d]
+    // work decomposition of the fibre kernel (filled by kron_plan): the axes other than `dim`
+    // split into "matrix" axes (mstride != 0; fixed per work item, so one factor matrix per item)
+    // and "free" axes (enumerated by the threads, innermost fastest)
+    int nF, nM;
+    int Fshape[SDFS_MAX_DIMS], Mshape[SDFS_MAX_DIMS], Mmat[SDFS_MAX_DIMS];
+    long long Fstride[SDFS_MAX_DIMS], Mstride[SDFS_MAX_DIMS];
+    long long stride, Fcount, Mcount;
 };
 struct KronView {
     int D;

@@ -206,6 +206,7 @@ __device__ __forceinline__ void store_all_ranks(const LoopEnv &env, int buf, int
 struct Scratch {
     RowPipe<1> *rp;        // TMA ring in dynamic shared memory (dense operators)
     PipeState st;
+    double *smat;          // factor matrix staging (factor-form operators), dynamic shared memory
 };
 
 struct DenseLoopOp {
@@ -231,10 +232,10 @@ struct DenseLoopOp {
 };
 
 struct KronLoopOp {
-    static constexpr int kMinBlocks = 2;
+    static constexpr int kMinBlocks = 1;
     KronView kv;
     double *tmp0, *tmp1;
-    __host__ __device__ size_t dyn_smem() const { return 0; }
+    __host__ __device__ size_t dyn_smem() const { return KRON_SMAT_DOUBLES * sizeof(double); }
     __device__ __forceinline__ void init(Scratch &) const {}
     __device__ __forceinline__ int64_t N() const { return kv.N; }
     __device__ __forceinline__ int64_t row_begin() const { return 0; }
@@ -245,17 +246,15 @@ struct KronLoopOp {
     __device__ __forceinline__ double theta() const { return kv.theta; }
     template <class Epi>
     __device__ __forceinline__ bool apply(cg::grid_group &grid, const LoopEnv &env, unsigned long long &epoch,
-                                          Scratch &, const double *xin, Epi &&epi) const {
-        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+                                          Scratch &sc, const double *xin, Epi &&epi) const {
         const double *in = xin;
         for (int m = 0; m < kv.n_modes - 1; ++m) {
             double *out = (m & 1) ? tmp1 : tmp0;
-            kron_mode_pass(kv, m, in, tid, nth, [&](int64_t idx, double s) { out[idx] = s; });
+            kron_mode_apply(kv, m, in, sc.smat, [&](int64_t idx, double s) { out[idx] = s; });
             if (!all_sync(grid, env, epoch)) return false;
             in = out;
         }
-        kron_mode_pass(kv, kv.n_modes - 1, in, tid, nth, [&](int64_t idx, double s) { epi(idx, s); });
+        kron_mode_apply(kv, kv.n_modes - 1, in, sc.smat, [&](int64_t idx, double s) { epi(idx, s); });
         return true;
     }
 };
@@ -280,6 +279,7 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_sa_loop(const 
     __shared__ double smem[SDFS_WARPS * NVAL + NVAL];
     Scratch sc;
     sc.rp = reinterpret_cast<RowPipe<1> *>(dyn_smem);
+    sc.smat = reinterpret_cast<double *>(dyn_smem);
     op.init(sc);
     unsigned long long epoch = env.epoch0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_newton_loop(co
     __shared__ double smem[SDFS_WARPS * NVAL + NVAL];
     Scratch sc;
     sc.rp = reinterpret_cast<RowPipe<1> *>(dyn_smem);
+    sc.smat = reinterpret_cast<double *>(dyn_smem);
     op.init(sc);
     __shared__ double hs[(GMRES_MAX_RESTART + 1) * 2 + GMRES_MAX_RESTART * 3 + GMRES_MAX_RESTART * GMRES_MAX_RESTART];
     unsigned long long epoch = env.epoch0;
@@ -773,9 +774,9 @@ int sdfs_solve_sa(sdfs_op *op, const double *d_w_init, double tol, int64_t max_i
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)op->kv.N * sizeof(double)));
         }
         KronLoopOp lop{op->kv, op->kron_tmp[0], op->kron_tmp[1]};
-        TRY(coop_grid(ctx, k_sa_loop<KronLoopOp>, 0, 2, (op->kv.N + SDFS_THREADS - 1) / SDFS_THREADS, false, &grid));
+        TRY(coop_grid(ctx, k_sa_loop<KronLoopOp>, lop.dyn_smem(), 2, (op->kv.N + SDFS_THREADS - 1) / SDFS_THREADS, false, &grid));
         void *args[] = {&lop, &a, &env};
-        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sa_loop<KronLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, 0, ctx->stream));
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sa_loop<KronLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, lop.dyn_smem(), ctx->stream));
     }
     ctx->launches++;
     LoopStatus *hs = (LoopStatus *)ctx->h_status;
@@ -832,9 +833,9 @@ int sdfs_solve_newton(sdfs_op *op, const double *d_w_init, double tol, int64_t m
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)N * sizeof(double)));
         }
         KronLoopOp lop{op->kv, op->kron_tmp[0], op->kron_tmp[1]};
-        TRY(coop_grid(ctx, k_newton_loop<KronLoopOp>, 0, 2, (N + SDFS_THREADS - 1) / SDFS_THREADS, false, &grid));
+        TRY(coop_grid(ctx, k_newton_loop<KronLoopOp>, lop.dyn_smem(), 2, (N + SDFS_THREADS - 1) / SDFS_THREADS, false, &grid));
         void *args[] = {&lop, &a, &env};
-        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_newton_loop<KronLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, 0, ctx->stream));
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_newton_loop<KronLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, lop.dyn_smem(), ctx->stream));
     }
     ctx->launches++;
     LoopStatus *hs = (LoopStatus *)ctx->h_status;

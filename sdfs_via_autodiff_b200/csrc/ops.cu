@@ -69,19 +69,19 @@ k_dense_apply(const __grid_constant__ DenseView dv, const double *x0, const doub
     dense_pass<NX>(dv, x0, x1, rp, st, [&](int64_t n, double s0, double s1) { apply_epilogue(e, n, s0, s1); });
 }
 
-__global__ void k_kron_mode(KronView kv, int m, const double *__restrict__ in, double *__restrict__ out) {
-    kron_mode_pass(kv, m, in, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x,
-                   [&](int64_t idx, double s) { out[idx] = s; });
+__global__ void __launch_bounds__(256) k_kron_mode(KronView kv, int m, const double *__restrict__ in, double *__restrict__ out) {
+    __shared__ __align__(16) double smat[KRON_SMAT_DOUBLES];
+    kron_mode_apply(kv, m, in, smat, [&](int64_t idx, double s) { out[idx] = s; });
 }
 // last mode of a two-vector apply: tmpA holds the finished s0 (or unused), the
 // contraction of `in` gives s1 (NX = 2) or s0 (NX = 1)
-__global__ void k_kron_last(KronView kv, int m, const double *__restrict__ in, const double *__restrict__ s0_done,
-                            EpiArgs e) {
-    kron_mode_pass(kv, m, in, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x,
-                   [&](int64_t idx, double s) {
-                       if (s0_done) apply_epilogue(e, idx, s0_done[idx], s);
-                       else apply_epilogue(e, idx, s, s);
-                   });
+__global__ void __launch_bounds__(256) k_kron_last(KronView kv, int m, const double *__restrict__ in,
+                                                   const double *__restrict__ s0_done, EpiArgs e) {
+    __shared__ __align__(16) double smat[KRON_SMAT_DOUBLES];
+    kron_mode_apply(kv, m, in, smat, [&](int64_t idx, double s) {
+        if (s0_done) apply_epilogue(e, idx, s0_done[idx], s);
+        else apply_epilogue(e, idx, s, s);
+    });
 }
 
 // 2-D TMA descriptor of the local row slice of P: dims (N columns, nloc rows), row pitch ld,
@@ -191,7 +191,8 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[0], (size_t)N * sizeof(double)));
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)N * sizeof(double)));
         }
-        const int grid = ew_grid(ctx, N);
+        // work items of the fibre kernel are distributed round-robin: any grid size is valid
+        const int grid = ctx->sm_count * 4;
         double *s0_done = nullptr;
         for (int pass = 0; pass < nx; ++pass) {
             const double *in = (pass == 0) ? x0 : x1;

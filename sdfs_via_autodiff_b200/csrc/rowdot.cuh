@@ -363,3 +363,78 @@ __device__ __forceinline__ void kron_mode_pass(const KronView &kv, int m, const 
         sink(idx, acc);
     }
 }
+
+// ---------------------------------------------------------------------------
+// Register-tiled mode contraction ("fibre" kernel).
+// A work item = (one combination of the matrix axes, a chunk of blockDim free-axis
+// combinations): all its fibres use the same n x n factor matrix, which is staged in
+// shared memory (rows zero-padded to NMAX) and read with broadcast LDS.128.  Each thread
+// loads its fibre (n inputs, stride = stride of the contracted axis) into registers,
+// forms the n outputs with n*NMAX FMAs and stores them (or feeds the epilogue).
+// Per fibre: n loads + n stores + n^2 FMAs, against 2 n^2 cached loads in kron_mode_pass.
+// Items are distributed round-robin over the CTAs (item -> CTA item mod grid), so the same
+// function serves plain launches and the persistent loop kernels.
+// ---------------------------------------------------------------------------
+#define KRON_NMAX_LIMIT 64
+template <int NMAX, class Sink>
+__device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const double *in, double *smat /* n*NMAX */,
+                                                Sink &&sink) {
+    const KronMode &md = kv.modes[m];
+    const int n = kv.shape[md.dim];
+    const long long chunks = (md.Fcount + blockDim.x - 1) / blockDim.x;
+    const long long items = md.Mcount * chunks;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long mc = item / chunks, chunk = item - mc * chunks;
+        // matrix axes -> matrix id and base offset
+        long long rem = mc, mbase = 0;
+        int mat = 0;
+        for (int a = md.nM - 1; a >= 0; --a) {
+            const int c = (int)(rem % md.Mshape[a]);
+            rem /= md.Mshape[a];
+            mat += c * md.Mmat[a];
+            mbase += c * md.Mstride[a];
+        }
+        __syncthreads();                        // previous item's matrix no longer in use
+        const double *msrc = md.mat + (long long)mat * n * n;
+        for (int e = threadIdx.x; e < n * NMAX; e += blockDim.x) {
+            const int i = e / NMAX, j = e - i * NMAX;
+            smat[e] = (j < n) ? msrc[i * n + j] : 0.0;
+        }
+        __syncthreads();
+        const long long f = chunk * blockDim.x + threadIdx.x;
+        if (f < md.Fcount) {
+            long long r2 = f, base = mbase;
+            for (int a = md.nF - 1; a >= 0; --a) {
+                const int c = (int)(r2 % md.Fshape[a]);
+                r2 /= md.Fshape[a];
+                base += c * md.Fstride[a];
+            }
+            double x[NMAX];
+#pragma unroll
+            for (int j = 0; j < NMAX; ++j) x[j] = (j < n) ? in[base + j * md.stride] : 0.0;
+            for (int i = 0; i < n; ++i) {
+                const double2 *row = reinterpret_cast<const double2 *>(smat + i * NMAX);
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NMAX / 2; ++j) {
+                    const double2 mv = row[j];
+                    a0 = fma(mv.x, x[2 * j], a0);
+                    a1 = fma(mv.y, x[2 * j + 1], a1);
+                }
+                sink(base + i * md.stride, a0 + a1);
+            }
+        }
+    }
+}
+
+// dispatch on the size of the contracted axis; falls back to the cached-load pass for n > 64
+template <class Sink>
+__device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const double *in, double *smat, Sink &&sink) {
+    const int n = kv.shape[kv.modes[m].dim];
+    if (n <= 8) kron_mode_fibre<8>(kv, m, in, smat, sink);
+    else if (n <= 16) kron_mode_fibre<16>(kv, m, in, smat, sink);
+    else if (n <= 32) kron_mode_fibre<32>(kv, m, in, smat, sink);
+    else if (n <= KRON_NMAX_LIMIT) kron_mode_fibre<64>(kv, m, in, smat, sink);
+    else kron_mode_pass(kv, m, in, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, sink);
+}
+#define KRON_SMAT_DOUBLES (KRON_NMAX_LIMIT * KRON_NMAX_LIMIT)
