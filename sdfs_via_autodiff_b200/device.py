@@ -46,6 +46,15 @@ def _capsule_destructor(capsule_ptr):
         lib.sdfs_dlpack_call_deleter(mt)
 
 
+_pinned_owners = {}
+
+
+def _release_pinned(key):
+    buf, ptr = _pinned_owners.pop(key, (None, None))
+    if ptr:
+        lib.sdfs_host_free_pinned(C.c_void_p(ptr))
+
+
 class Context:
     """One GPU, one stream.  ``Context.default()`` is created lazily on device
     ``LOCAL_RANK`` (or 0)."""
@@ -104,6 +113,20 @@ class Context:
         a = DeviceArray._alloc(self, shape)
         check(lib.sdfs_fill_f64(self.handle, a.ptr, float(value), a.size), self.handle)
         return a
+
+    def pinned_empty(self, shape):
+        """Host ndarray backed by page-locked memory (cudaMallocHost): h2d/d2h copies of such
+        arrays are true DMA transfers.  The memory is released when the array is collected."""
+        shape = tuple(int(s) for s in (shape if hasattr(shape, "__len__") else (shape,)))
+        n = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        p = C.c_void_p()
+        check(lib.sdfs_host_alloc_pinned(n * 8, C.byref(p)))
+        buf = (C.c_double * n).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.float64).reshape(shape)
+        _pinned_owners[id(buf)] = (buf, p.value)
+        import weakref
+        weakref.finalize(arr, _release_pinned, id(buf))
+        return arr
 
     def asarray(self, x):
         """Host ndarray / DLPack producer / DeviceArray -> DeviceArray on this context."""
@@ -166,8 +189,13 @@ class DeviceArray:
     def ndim(self):
         return len(self.shape)
 
-    def numpy(self):
-        out = np.empty(self.shape, dtype=np.float64)
+    def numpy(self, out=None):
+        """Download.  ``out`` (optional): a C-contiguous float64 host array of the same size,
+        e.g. a pinned buffer from Context.pinned_empty."""
+        if out is None:
+            out = np.empty(self.shape, dtype=np.float64)
+        elif out.size != self.size or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of the same size")
         check(lib.sdfs_d2h(self.ctx.handle, out.ctypes.data, self.ptr, out.nbytes), self.ctx.handle)
         return out
 

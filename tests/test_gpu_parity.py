@@ -299,6 +299,30 @@ def test_sweep_batched_T_and_solve():
     assert list(iters) == [7, 7]
 
 
+def test_error_behaviour_and_pinned_buffers():
+    ctx = S.Context.default()
+    # dense P that cannot fit: a clear out-of-memory error, not a crash (8.8 TB at 10^6 states)
+    with pytest.raises(S.SdfsError) as ei:
+        S.make_T_ssy(S.SSY(), (32, 32, 32, 32), storage="dense")
+    assert ei.value.code == -3 and "GB" in str(ei.value)
+    with pytest.raises(S.SdfsError):
+        S.make_T_ssy(S.SSY(), (1, 3, 4, 5))                    # every axis needs >= 2 states
+    with pytest.raises(ValueError):
+        S.make_T_ssy(S.SSY(), (2, 3, 4, 5), arrays=O.discretize_ssy(O.SSY(), (2, 3, 4, 6)))
+    op = S.make_T_ssy(S.SSY(), (2, 3, 4, 5))
+    with pytest.raises(KeyError):
+        S.newton_solver(op, np.full(op.shapes, 800.0), krylov="cg", verbose=False)
+    # pinned host buffers round trip
+    h = ctx.pinned_empty(op.shapes)
+    h[...] = 800.0
+    out = ctx.pinned_empty(op.shapes)
+    got = op(h).numpy(out=out)
+    assert got is out
+    np.testing.assert_array_equal(out, np.asarray(op(np.full(op.shapes, 800.0))))
+    with pytest.raises(ValueError):
+        op(h).numpy(out=np.empty(3))
+
+
 def test_dlpack_roundtrip_with_torch():
     torch = pytest.importorskip("torch")
     ctx = S.Context.default()
