@@ -98,6 +98,33 @@ def test_from_dense_ragged_sizes(N):
                                rtol=1e-11, atol=1e-13)
 
 
+@pytest.mark.parametrize("N,ld", [(1001, 1002), (257, 320), (513, 514), (255, 256), (2, 2), (9, 16)])
+def test_from_dense_padded_leading_dimension(N, ld):
+    """TMA path with N != ld: the padding columns hold NaN and must never be read as data
+    (the tensor map is N columns wide, everything outside is zero-filled by the TMA unit)."""
+    rng = np.random.default_rng(N + ld)
+    P = rng.random((N, N))
+    P /= P.sum(1, keepdims=True)
+    Ppad = np.full((N, ld), np.nan)
+    Ppad[:, :N] = P
+    a_row, a_col = 0.5 + rng.random(N), 0.5 + rng.random(N)
+    β, θ = 0.98, -5.3
+    w = 1.0 + 5 * rng.random(N)
+    op = S.WCOperator.from_dense(Ppad, a_row, a_col, β, θ)
+    assert op.ld == ld
+    np.testing.assert_allclose(np.asarray(op(w)), O.dense_T(w, P, a_row, a_col, β, θ), rtol=RTOL_T)
+    v = rng.standard_normal(N)
+    np.testing.assert_allclose(np.asarray(op.jvp(w, v)), O.dense_jvp(w, v, P, a_row, a_col, β, θ),
+                               rtol=1e-11, atol=1e-13)
+    ws, k = S.successive_approx(op, w, tol=1e-9, max_iter=500, verbose=False)
+    ref = w.copy()
+    for _ in range(k):
+        ref = O.dense_T(ref, P, a_row, a_col, β, θ)
+    np.testing.assert_allclose(np.asarray(ws), ref, rtol=1e-11)
+    wn, kn = S.newton_solver(op, w, tol=1e-10, bicgstab_atol=1e-12, krylov_rtol=1e-13, verbose=False)
+    np.testing.assert_allclose(np.asarray(wn), O.dense_T(np.asarray(wn), P, a_row, a_col, β, θ), rtol=1e-10)
+
+
 def test_jvp_matches_oracle_both_storages():
     ssy = O.SSY()
     shapes = (4, 7, 6, 5)
