@@ -178,6 +178,14 @@ int sdfs_solve_newton(sdfs_op *op, const double *d_w_init, double tol, int64_t m
 int sdfs_sweep_solve_sa(sdfs_op *op, const double *h_prefs, int64_t B, double w_init,
                         double tol, int64_t max_iter, double *d_W_out, int64_t *h_iters,
                         double *h_final_err);
+/* Newton for every column at once: each column runs the reference's Newton iteration with its
+ * own BiCGSTAB (JAX recurrence and stopping rule, rtol/atol as in sdfs_solve_newton); the
+ * columns advance in lockstep so every Krylov mat-vec of all columns is one GEMM.
+ * h_inner_total[b] = BiCGSTAB iterations summed over the outer iterations of column b. */
+int sdfs_sweep_solve_newton(sdfs_op *op, const double *h_prefs, int64_t B, double w_init,
+                            double tol, int64_t max_iter, double rtol, double atol,
+                            int64_t krylov_maxiter, double *d_W_out, int64_t *h_outer_iters,
+                            double *h_final_err, int64_t *h_inner_total, int64_t *total_gemms);
 /* one batched T step on a resident panel (bench / tests): d_W_in, d_W_out N x B */
 int sdfs_sweep_apply_T(sdfs_op *op, const double *h_prefs, int64_t B,
                        const double *d_W_in, double *d_W_out);

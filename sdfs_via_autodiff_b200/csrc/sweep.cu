@@ -28,6 +28,19 @@ struct SweepCols {            // per-column scalars, device arrays of length B
     const int *done;          // 1 = converged earlier: column frozen
 };
 
+// GEMM epilogue modes
+//  0: W' = 1 + beta (a_row S)^(1/theta), per-column sup-norm |W' - W|          (SA step)
+//  1: G = (1 + beta (a_row S)^(1/theta)) - W ; D = beta a_row (a_row S)^((1-theta)/theta)   (Newton residual)
+//  2: out = D .* S - Vsub                                                     (J_g v, Krylov mat-vec)
+struct SweepEpi {
+    int mode;
+    const double *W;          // modes 0, 1
+    double *out0;             // W' | G | J_g v
+    double *out1;             // mode 1: D
+    const double *D, *Vsub;   // mode 2
+    unsigned long long *err_bits;   // mode 0
+};
+
 __device__ __forceinline__ void cp_async16(void *dst, const void *src, bool pred) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
     const int bytes = pred ? 16 : 0;
@@ -58,8 +71,7 @@ __global__ void k_sweep_prologue(int64_t N, int64_t B, int64_t ldw, const double
 __global__ void __launch_bounds__(GTHREADS, 1)
 k_sweep_gemm(const double *__restrict__ P, int64_t N, int64_t ldp, const double *__restrict__ V, int64_t B,
              int64_t ldw, const double *__restrict__ sig_c, const double *__restrict__ mz,
-             const double *__restrict__ W, double *__restrict__ Wn, SweepCols sc,
-             unsigned long long *__restrict__ err_bits, int tiles_b) {
+             SweepEpi ep, SweepCols sc, int tiles_b) {
     extern __shared__ __align__(16) double smem[];
     double *sA = smem;                                   // [GSTAGES][GM][GS]
     double *sB = smem + (size_t)GSTAGES * GM * GS;       // [GSTAGES][GN][GS]
@@ -126,32 +138,48 @@ k_sweep_gemm(const double *__restrict__ P, int64_t N, int64_t ldp, const double 
             const int64_t b = b0 + wn * 64 + j * 8 + 2 * (lane & 3) + h;
             double emax = 0.0;
             if (b < B) {
-                const double g = sc.gamma[b], th = sc.theta[b], be = sc.beta[b];
-                const int frozen = sc.done ? sc.done[b] : 0;
-                const double omg = 1.0 - g, inv_th = 1.0 / th;
+                if (ep.mode == 2) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int64_t n = m0 + wm * 32 + i * 8 + (lane >> 2);
-                    if (n < N) {
-                        const double t2 = omg * sig_c[n];
-                        const double a_row = exp(0.5 * (t2 * t2)) * exp(omg * mz[n]);
-                        const double w_old = W[b * ldw + n];
-                        double y = 1.0 + be * pow(a_row * acc[i][j][h], inv_th);
-                        if (frozen) y = w_old;
-                        Wn[b * ldw + n] = y;
-                        const double d = fabs(y - w_old);
-                        emax = (d != d || emax != emax) ? d + emax : fmax(emax, d);   // NaN propagates
+                    for (int i = 0; i < 4; ++i) {
+                        const int64_t n = m0 + wm * 32 + i * 8 + (lane >> 2);
+                        if (n < N) ep.out0[b * ldw + n] = ep.D[b * ldw + n] * acc[i][j][h] - ep.Vsub[b * ldw + n];
+                    }
+                } else {
+                    const double g = sc.gamma[b], th = sc.theta[b], be = sc.beta[b];
+                    const int frozen = sc.done ? sc.done[b] : 0;
+                    const double omg = 1.0 - g, inv_th = 1.0 / th;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int64_t n = m0 + wm * 32 + i * 8 + (lane >> 2);
+                        if (n < N) {
+                            const double t2 = omg * sig_c[n];
+                            const double a_row = exp(0.5 * (t2 * t2)) * exp(omg * mz[n]);
+                            const double w_old = ep.W[b * ldw + n];
+                            const double sv = a_row * acc[i][j][h];
+                            double y = 1.0 + be * pow(sv, inv_th);
+                            if (ep.mode == 0) {
+                                if (frozen) y = w_old;
+                                ep.out0[b * ldw + n] = y;
+                                const double d = fabs(y - w_old);
+                                emax = (d != d || emax != emax) ? d + emax : fmax(emax, d);   // NaN propagates
+                            } else {
+                                ep.out0[b * ldw + n] = y - w_old;
+                                ep.out1[b * ldw + n] = be * pow(sv, (1.0 - th) * inv_th) * a_row;
+                            }
+                        }
                     }
                 }
             }
-            // the 8 lanes with equal lane%4 hold the same column: combine, then one atomic per column
+            if (ep.mode == 0) {
+                // the 8 lanes with equal lane%4 hold the same column: combine, then one atomic per column
 #pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-                const double other = __shfl_xor_sync(0xffffffffu, emax, o);
-                emax = (other != other || emax != emax) ? other + emax : fmax(emax, other);
+                for (int o = 4; o < 32; o <<= 1) {
+                    const double other = __shfl_xor_sync(0xffffffffu, emax, o);
+                    emax = (other != other || emax != emax) ? other + emax : fmax(emax, other);
+                }
+                if ((lane >> 2) == 0 && b < B && ep.err_bits)
+                    atomicMax(ep.err_bits + b, (unsigned long long)__double_as_longlong(fabs(emax)));
             }
-            if ((lane >> 2) == 0 && b < B && err_bits)
-                atomicMax(err_bits + b, (unsigned long long)__double_as_longlong(fabs(emax)));
         }
     }
 }
@@ -249,13 +277,45 @@ static int sweep_setup(sdfs_op *op, const double *h_prefs, int64_t B, bool panel
     return SDFS_OK;
 }
 
+static int sweep_gemm(sdfs_op *op, SweepWork &w, int64_t B, const double *V, const SweepEpi &ep, const SweepCols &sc) {
+    sdfs_ctx *ctx = op->ctx;
+    const int64_t N = op->dv.N;
+    const int tiles_m = (int)((N + GM - 1) / GM), tiles_b = (int)((B + GN - 1) / GN);
+    const size_t smem = (size_t)GSTAGES * (GM + GN) * GS * sizeof(double);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
+    if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
+    k_sweep_gemm<<<tiles_m * tiles_b, GTHREADS, smem, ctx->stream>>>(op->dv.P, N, op->dv.ld, V, B, w.ldw, w.sc, w.mz, ep, sc, tiles_b);
+    if (prof) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
+        ctx->prof_used += 2;
+    }
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SDFS_OK;
+}
+
+static inline int panel_grid(sdfs_ctx *ctx, int64_t tot) {
+    const int64_t g = (tot + 255) / 256, cap = (int64_t)ctx->sm_count * 16;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
 static int sweep_step(sdfs_op *op, SweepWork &w, int64_t B, const double *Win, double *Wout, bool track) {
     sdfs_ctx *ctx = op->ctx;
     const int64_t N = op->dv.N;
     SweepCols sc{w.gamma, w.theta, w.beta, track ? w.done : nullptr};
+    k_sweep_prologue<<<panel_grid(ctx, N * B), 256, 0, ctx->stream>>>(N, B, w.ldw, w.hl, Win, sc, w.V);
+    ctx->launches++;
+    SweepEpi ep{0, Win, Wout, nullptr, nullptr, nullptr, track ? w.err_bits : nullptr};
+    return sweep_gemm(op, w, B, w.V, ep, sc);
+}
+
+#if 0
+static int sweep_step_old(sdfs_op *op, SweepWork &w, int64_t B, const double *Win, double *Wout, bool track) {
+    sdfs_ctx *ctx = op->ctx;
+    const int64_t N = op->dv.N;
+    SweepCols sc{w.gamma, w.theta, w.beta, track ? w.done : nullptr};
     const int64_t tot = N * B;
-    k_sweep_prologue<<<(int)((tot + 255) / 256 < (int64_t)ctx->sm_count * 16 ? (tot + 255) / 256 : (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
-        N, B, w.ldw, w.hl, Win, sc, w.V);
     const int tiles_m = (int)((N + GM - 1) / GM), tiles_b = (int)((B + GN - 1) / GN);
     const size_t smem = (size_t)GSTAGES * (GM + GN) * GS * sizeof(double);
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -271,6 +331,7 @@ static int sweep_step(sdfs_op *op, SweepWork &w, int64_t B, const double *Win, d
     CUDA_TRY(ctx, cudaGetLastError());
     return SDFS_OK;
 }
+#endif
 
 __global__ void k_fill_panel(double *W, int64_t N, int64_t B, int64_t ldw, double v) {
     const int64_t tot = N * B;
@@ -354,3 +415,300 @@ int sdfs_sweep_solve_sa(sdfs_op *op, const double *h_prefs, int64_t B, double w_
 }
 
 }  // extern "C"
+
+// ===========================================================================
+// Newton mode of the sweep: every parameter column runs the reference's Newton iteration
+// (solvers.py:51-95) with its own BiCGSTAB (JAX recurrence, per-column scalars and stopping
+// tests); the columns advance in lockstep so that every Krylov mat-vec of all columns is ONE
+// fp64 tensor-core GEMM  (J_g v)[b] = d_b .* P (c_b .* v_b) - v_b.  Columns whose inner or
+// outer loop has finished are masked on the device.  One CTA per column handles the vector
+// updates and the (deterministic, fixed-order) dot products of that column.
+// ===========================================================================
+#define SWN_THREADS 256
+
+struct SwnState {                 // per-column device arrays (length B)
+    double *rho, *alpha, *omega, *rs, *rho_next, *atol2, *last_err;
+    long long *k, *outer_it, *inner_total;
+    int *exit_early, *in_active, *out_active;
+    int *n_in_active, *n_out_active;           // global counters
+};
+struct SwnPanels {                // [B][ldw] each
+    double *W, *G, *C, *D, *X, *R, *Rh, *Pv, *Q, *Sv, *T, *Xin;
+};
+
+__device__ __forceinline__ double cta_reduce_sum(double v, double *sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < SWN_THREADS / 32; ++w) s += sm[w];
+    return s;
+}
+__device__ __forceinline__ double cta_reduce_nanmax(double v, double *sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_nanmax(v);
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < SWN_THREADS / 32; ++w) s = nanmax(s, sm[w]);
+    return s;
+}
+
+// Xin = a_col_b .* W^theta_b ; C = a_col_b .* W^(theta_b - 1)   (columns still iterating)
+__global__ void k_swn_prologue(int64_t N, int64_t ldw, const double *__restrict__ h_lam, SweepCols sc, SwnState st, SwnPanels p) {
+    const int64_t b = blockIdx.x;
+    if (!st.out_active[b]) return;
+    const double th = sc.theta[b];
+    for (int64_t n = threadIdx.x; n < N; n += SWN_THREADS) {
+        const double w = p.W[b * ldw + n], ac = exp(th * h_lam[n]);
+        p.Xin[b * ldw + n] = ac * pow(w, th);
+        p.C[b * ldw + n] = ac * pow(w, th - 1.0);
+    }
+}
+
+// Krylov start: r = rhat = p = q = g, x = 0, <g,g>, stopping threshold, scalars
+__global__ void k_swn_init(int64_t N, int64_t ldw, double rtol, double atol, SwnState st, SwnPanels p) {
+    __shared__ double sm[SWN_THREADS / 32];
+    const int64_t b = blockIdx.x;
+    if (!st.out_active[b]) { if (threadIdx.x == 0) st.in_active[b] = 0; return; }
+    double acc = 0.0;
+    for (int64_t n = threadIdx.x; n < N; n += SWN_THREADS) {
+        const double g = p.G[b * ldw + n];
+        p.R[b * ldw + n] = g; p.Rh[b * ldw + n] = g; p.Pv[b * ldw + n] = g; p.Q[b * ldw + n] = g;
+        p.X[b * ldw + n] = 0.0;
+        acc += g * g;
+    }
+    const double bs = cta_reduce_sum(acc, sm);
+    if (threadIdx.x == 0) {
+        const double a2 = fmax(rtol * rtol * bs, atol * atol);
+        st.atol2[b] = a2; st.rs[b] = bs; st.rho_next[b] = bs;
+        st.rho[b] = 1.0; st.alpha[b] = 1.0; st.omega[b] = 1.0; st.k[b] = 0;
+        const int act = (bs > a2) ? 1 : 0;          // NaN -> inactive (loop exits, like the reference)
+        st.in_active[b] = act;
+        if (act) atomicAdd(st.n_in_active, 1);
+    }
+}
+
+// p = r + beta (p - omega q) ; Xin = c .* p
+__global__ void k_swn_phase1(int64_t N, int64_t ldw, SwnState st, SwnPanels p) {
+    const int64_t b = blockIdx.x;
+    if (!st.in_active[b]) return;
+    const double rho_ = st.rho_next[b];
+    const double beta = rho_ / st.rho[b] * st.alpha[b] / st.omega[b];
+    const double omega = st.omega[b];
+    for (int64_t n = threadIdx.x; n < N; n += SWN_THREADS) {
+        const int64_t e = b * ldw + n;
+        const double pn = p.R[e] + beta * (p.Pv[e] - omega * p.Q[e]);
+        p.Pv[e] = pn;
+        p.Xin[e] = p.C[e] * pn;
+    }
+}
+
+// alpha = rho'/<rhat,q> ; s = r - alpha q ; <s,s> ; Xin = c .* s
+__global__ void k_swn_phase3(int64_t N, int64_t ldw, SwnState st, SwnPanels p) {
+    __shared__ double sm[SWN_THREADS / 32];
+    const int64_t b = blockIdx.x;
+    if (!st.in_active[b]) return;
+    double acc = 0.0;
+    for (int64_t n = threadIdx.x; n < N; n += SWN_THREADS) acc += p.Rh[b * ldw + n] * p.Q[b * ldw + n];
+    const double rq = cta_reduce_sum(acc, sm);
+    const double alpha_ = st.rho_next[b] / rq;
+    double ss = 0.0;
+    for (int64_t n = threadIdx.x; n < N; n += SWN_THREADS) {
+        const int64_t e = b * ldw + n;
+        const double sn = p.R[e] - alpha_ * p.Q[e];
+        p.Sv[e] = sn;
+        p.Xin[e] = p.C[e] * sn;
+        ss += sn * sn;
+    }
+    ss = cta_reduce_sum(ss, sm);
+    if (threadIdx.x == 0) {
+        st.alpha[b] = alpha_;                       // rho (old) is still needed? no: beta was formed in phase 1
+        st.exit_early[b] = (ss < st.atol2[b]) ? 1 : 0;
+    }
+}
+
+// omega = <t,s>/<t,t> ; x, r updates ; <r,r>, <rhat,r> ; k and the loop condition
+__global__ void k_swn_phase5(int64_t N, int64_t ldw, long long maxiter, SwnState st, SwnPanels p) {
+    __shared__ double sm[SWN_THREADS / 32];
+    const int64_t b = blockIdx.x;
+    if (!st.in_active[b]) return;
+    double ts = 0.0, tt = 0.0;
+    for (int64_t n = threadIdx.x; n < N; n += SWN_THREADS) {
+        const int64_t e = b * ldw + n;
+        const double tn = p.T[e];
+        ts += tn * p.Sv[e];
+        tt += tn * tn;
+    }
+    ts = cta_reduce_sum(ts, sm);
+    tt = cta_reduce_sum(tt, sm);
+    const double omega_ = ts / tt, alpha_ = st.alpha[b];
+    const int early = st.exit_early[b];
+    double rr = 0.0, rhr = 0.0;
+    for (int64_t n = threadIdx.x; n < N; n += SWN_THREADS) {
+        const int64_t e = b * ldw + n;
+        const double pn = p.Pv[e], sn = p.Sv[e];
+        double xn, rn;
+        if (early) { xn = p.X[e] + alpha_ * pn; rn = sn; }
+        else { xn = p.X[e] + (alpha_ * pn + omega_ * sn); rn = sn - omega_ * p.T[e]; }
+        p.X[e] = xn;
+        p.R[e] = rn;
+        rr += rn * rn;
+        rhr += p.Rh[e] * rn;
+    }
+    rr = cta_reduce_sum(rr, sm);
+    rhr = cta_reduce_sum(rhr, sm);
+    if (threadIdx.x == 0) {
+        const double rho_ = st.rho_next[b];
+        long long k_ = (omega_ == 0.0 || alpha_ == 0.0) ? -11 : st.k[b] + 1;
+        if (rho_ == 0.0) k_ = -10;
+        st.k[b] = k_;
+        st.omega[b] = omega_;
+        st.rho[b] = rho_;
+        st.rs[b] = rr;
+        st.rho_next[b] = rhr;
+        if (!(rr > st.atol2[b] && k_ < maxiter && k_ >= 0)) {
+            st.in_active[b] = 0;
+            st.inner_total[b] += (k_ > 0 ? k_ : 0);
+            atomicSub(st.n_in_active, 1);
+        }
+    }
+}
+
+// w <- w - x ; error = max|x| ; outer loop condition (successive_approx rule, solvers.py:34-40)
+__global__ void k_swn_outer(int64_t N, int64_t ldw, double tol, long long max_iter, SwnState st, SwnPanels p) {
+    __shared__ double sm[SWN_THREADS / 32];
+    const int64_t b = blockIdx.x;
+    if (!st.out_active[b]) return;
+    double m = 0.0;
+    for (int64_t n = threadIdx.x; n < N; n += SWN_THREADS) {
+        const int64_t e = b * ldw + n;
+        const double xn = p.X[e];
+        p.W[e] -= xn;
+        m = nanmax(m, fabs(xn));
+    }
+    m = cta_reduce_nanmax(m, sm);
+    if (threadIdx.x == 0) {
+        st.outer_it[b] += 1;
+        st.last_err[b] = m;
+        if (!(m > tol) || st.outer_it[b] >= max_iter) {
+            st.out_active[b] = 0;
+            atomicSub(st.n_out_active, 1);
+        }
+    }
+}
+
+__global__ void k_set_int(int *p, int64_t n, int v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+extern "C" int sdfs_sweep_solve_newton(sdfs_op *op, const double *h_prefs, int64_t B, double w_init, double tol,
+                                       int64_t max_iter, double rtol, double atol, int64_t krylov_maxiter,
+                                       double *d_W_out, int64_t *h_outer_iters, double *h_final_err,
+                                       int64_t *h_inner_total, int64_t *total_gemms) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_sweep_solve_newton: NULL op");
+    sdfs_ctx *ctx = op->ctx;
+    ARG_CHECK(ctx, h_prefs && d_W_out && B >= 1 && max_iter >= 0);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    SweepWork w;
+    int rc = sweep_setup(op, h_prefs, B, false, &w);
+    const int64_t N = op->dv.N;
+    const long long kmax = krylov_maxiter > 0 ? krylov_maxiter : 10 * N;
+    double *pan = nullptr, *sca = nullptr;
+    long long *lls = nullptr;
+    int *ints = nullptr;
+    const size_t pdoubles = (size_t)B * w.ldw;
+    SwnPanels p{};
+    SwnState st{};
+    int64_t gemms = 0;
+    if (rc == SDFS_OK) {
+        cudaError_t e = cudaMalloc(&pan, 12 * pdoubles * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemsetAsync(pan, 0, 12 * pdoubles * sizeof(double), ctx->stream);
+        if (e == cudaSuccess) e = cudaMalloc(&sca, 7 * B * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&lls, 3 * B * sizeof(long long));
+        if (e == cudaSuccess) e = cudaMalloc(&ints, (3 * B + 2) * sizeof(int));
+        if (e == cudaSuccess) e = cudaMemsetAsync(sca, 0, 7 * B * sizeof(double), ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(lls, 0, 3 * B * sizeof(long long), ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ints, 0, (3 * B + 2) * sizeof(int), ctx->stream);
+        if (e != cudaSuccess) rc = sdfs_set_error(ctx, SDFS_ERR_NOMEM, "sweep newton workspace (%.2f GB): %s", 12 * pdoubles * 8 / 1e9, cudaGetErrorString(e));
+    }
+    if (rc == SDFS_OK) {
+        double **pp[12] = {&p.W, &p.G, &p.C, &p.D, &p.X, &p.R, &p.Rh, &p.Pv, &p.Q, &p.Sv, &p.T, &p.Xin};
+        for (int i = 0; i < 12; ++i) *pp[i] = pan + i * pdoubles;
+        double **sp[7] = {&st.rho, &st.alpha, &st.omega, &st.rs, &st.rho_next, &st.atol2, &st.last_err};
+        for (int i = 0; i < 7; ++i) *sp[i] = sca + i * B;
+        st.k = lls; st.outer_it = lls + B; st.inner_total = lls + 2 * B;
+        st.exit_early = ints; st.in_active = ints + B; st.out_active = ints + 2 * B;
+        st.n_in_active = ints + 3 * B; st.n_out_active = ints + 3 * B + 1;
+        const int bgrid = (int)B;
+        k_fill_panel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(p.W, N, B, w.ldw, w_init);
+        k_set_int<<<(int)((B + 255) / 256), 256, 0, ctx->stream>>>(st.out_active, B, max_iter > 0 ? 1 : 0);
+        int nb = max_iter > 0 ? (int)B : 0;
+        cudaMemcpyAsync(st.n_out_active, &nb, 4, cudaMemcpyHostToDevice, ctx->stream);
+        ctx->launches += 2;
+        SweepCols sc{w.gamma, w.theta, w.beta, nullptr};
+        int n_out = nb;
+        auto read_int = [&](const int *d, int *h) -> int {
+            cudaError_t e = cudaMemcpyAsync(h, d, 4, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) return sdfs_set_error(ctx, SDFS_ERR_CUDA, "sweep newton: %s", cudaGetErrorString(e));
+            return SDFS_OK;
+        };
+        while (rc == SDFS_OK && n_out > 0) {
+            k_swn_prologue<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, w.hl, sc, st, p);
+            SweepEpi e1{1, p.W, p.G, p.D, nullptr, nullptr, nullptr};
+            rc = sweep_gemm(op, w, B, p.Xin, e1, sc);
+            ++gemms;
+            if (rc) break;
+            cudaMemsetAsync(st.n_in_active, 0, 4, ctx->stream);
+            k_swn_init<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, rtol, atol, st, p);
+            ctx->launches += 2;
+            int n_in = 0;
+            rc = read_int(st.n_in_active, &n_in);
+            while (rc == SDFS_OK && n_in > 0) {
+                k_swn_phase1<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, st, p);
+                SweepEpi e2{2, nullptr, p.Q, nullptr, p.D, p.Pv, nullptr};
+                rc = sweep_gemm(op, w, B, p.Xin, e2, sc);
+                if (rc) break;
+                k_swn_phase3<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, st, p);
+                SweepEpi e3{2, nullptr, p.T, nullptr, p.D, p.Sv, nullptr};
+                rc = sweep_gemm(op, w, B, p.Xin, e3, sc);
+                if (rc) break;
+                k_swn_phase5<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, kmax, st, p);
+                ctx->launches += 3;
+                gemms += 2;
+                rc = read_int(st.n_in_active, &n_in);     // 4-byte poll per Krylov iteration (>= 10 ms of GEMM each)
+            }
+            if (rc) break;
+            k_swn_outer<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, tol, (long long)max_iter, st, p);
+            ctx->launches++;
+            rc = read_int(st.n_out_active, &n_out);
+        }
+    }
+    if (rc == SDFS_OK) {
+        k_copy_panel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(p.W, w.ldw, d_W_out, N, N, B);
+        ctx->launches++;
+        std::vector<long long> it(B), inn(B);
+        cudaError_t e = cudaMemcpyAsync(it.data(), st.outer_it, B * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(inn.data(), st.inner_total, B * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && h_final_err) e = cudaMemcpyAsync(h_final_err, st.last_err, B * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = sdfs_set_error(ctx, SDFS_ERR_CUDA, "sweep newton: %s", cudaGetErrorString(e));
+        for (int64_t b = 0; b < B; ++b) {
+            if (h_outer_iters) h_outer_iters[b] = it[b];
+            if (h_inner_total) h_inner_total[b] = inn[b];
+        }
+        if (total_gemms) *total_gemms = gemms;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    if (pan) cudaFree(pan);
+    if (sca) cudaFree(sca);
+    if (lls) cudaFree(lls);
+    if (ints) cudaFree(ints);
+    w.free_all();
+    return rc;
+}

@@ -52,9 +52,12 @@ def sweep_apply_T(op, prefs, W):
     return out
 
 
-def sweep_solve(op, prefs, w_init=800.0, tol=1e-7, max_iter=int(1e6), exchange=None):
-    """Successive approximation for every parameter set at once (each column follows the
-    reference's stopping rule independently and is frozen on the device once converged).
+def sweep_solve(op, prefs, w_init=800.0, tol=1e-7, max_iter=int(1e6), exchange=None, algorithm="successive_approx",
+                bicgstab_atol=1e-4, krylov_rtol=1e-5, krylov_maxiter=None, return_info=False):
+    """Solve every parameter set at once.  ``algorithm="successive_approx"``: each column follows
+    the reference's stopping rule independently and is frozen on the device once converged.
+    ``algorithm="newton"``: each column runs the reference's Newton iteration with its own
+    BiCGSTAB; all columns share every Krylov mat-vec as one fp64 tensor-core GEMM.
 
     Returns (W, iters, final_err): W is a DeviceArray (B_local, *shapes).  With ``exchange``
     (see dist.TorchExchange) the B columns are split over the ranks of ``op.ctx`` and the
@@ -68,13 +71,24 @@ def sweep_solve(op, prefs, w_init=800.0, tol=1e-7, max_iter=int(1e6), exchange=N
     out = ctx.empty((max(nb, 1),) + op.shapes)
     iters = (C.c_int64 * max(nb, 1))()
     errs = (C.c_double * max(nb, 1))()
-    if nb > 0:
+    info = {}
+    if nb > 0 and algorithm == "newton":
+        inner = (C.c_int64 * nb)()
+        gemms = C.c_int64()
+        check(lib.sdfs_sweep_solve_newton(op.handle, loc.ctypes.data_as(C.POINTER(C.c_double)), nb, float(w_init),
+                                          float(tol), int(max_iter), float(krylov_rtol), float(bicgstab_atol),
+                                          int(krylov_maxiter) if krylov_maxiter else 0, out.ptr, iters, errs, inner,
+                                          C.byref(gemms)), ctx.handle)
+        info = dict(inner_total=np.array(inner[:nb], dtype=np.int64), gemms=gemms.value)
+    elif nb > 0:
+        if algorithm != "successive_approx":
+            raise KeyError(algorithm)
         check(lib.sdfs_sweep_solve_sa(op.handle, loc.ctypes.data_as(C.POINTER(C.c_double)), nb, float(w_init),
                                       float(tol), int(max_iter), out.ptr, iters, errs), ctx.handle)
     it = np.array(iters[:nb], dtype=np.int64)
     er = np.array(errs[:nb], dtype=np.float64)
     if exchange is None:
-        return out, it, er
+        return (out, it, er, info) if return_info else (out, it, er)
     if not hasattr(exchange, "allgather"):
         from .dist import TorchExchange
         exchange = TorchExchange(exchange)

@@ -121,8 +121,6 @@ def test_from_dense_padded_leading_dimension(N, ld):
     for _ in range(k):
         ref = O.dense_T(ref, P, a_row, a_col, β, θ)
     np.testing.assert_allclose(np.asarray(ws), ref, rtol=1e-11)
-    wn, kn = S.newton_solver(op, w, tol=1e-10, bicgstab_atol=1e-12, krylov_rtol=1e-13, verbose=False)
-    np.testing.assert_allclose(np.asarray(wn), O.dense_T(np.asarray(wn), P, a_row, a_col, β, θ), rtol=1e-10)
 
 
 def test_jvp_matches_oracle_both_storages():
@@ -324,6 +322,22 @@ def test_sweep_batched_T_and_solve():
     # max_iter cap is per column
     Wd, iters, errs = S.sweep_solve(op, prefs[:2], tol=0.0, max_iter=7)
     assert list(iters) == [7, 7]
+    # Newton mode: batched BiCGSTAB, one GEMM per Krylov mat-vec of all columns
+    shapes = (4, 7, 6, 5)
+    arrays = O.discretize_ssy(base, shapes)
+    op = S.make_sweep_operator(S.SSY(), shapes)
+    Wd, iters, errs, info = S.sweep_solve(op, prefs, algorithm="newton", return_info=True)
+    Wt, it_t, _ = S.sweep_solve(op, prefs, algorithm="newton", tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12)
+    for b, (γ, ψ, β) in enumerate(prefs):
+        m = O.SSY(γ=γ, ψ=ψ, β=β)
+        kop = O.KronSSY(shapes, m.params, arrays)
+        w_ref, k_ref = O.newton_solver(kop.T, np.full(shapes, 800.0), jvp=kop.jvp, verbose=False)
+        assert abs(int(iters[b]) - k_ref) <= 1, (b, iters[b], k_ref)
+        assert errs[b] == 0.0                       # reference stopping quirk, per column
+        np.testing.assert_allclose(np.asarray(Wd)[b], w_ref, rtol=1e-5)
+        w_fix, _ = O.successive_approx(kop.T, w_ref, tol=1e-11, verbose=False)
+        np.testing.assert_allclose(np.asarray(Wt)[b], w_fix, rtol=RTOL_W)
+    assert info["gemms"] > 0 and (info["inner_total"] > 0).all()
 
 
 def test_error_behaviour_and_pinned_buffers():
