@@ -13,6 +13,7 @@ int sdfs_set_error(sdfs_ctx *ctx, int code, const char *fmt, ...) {
     va_end(ap);
     if (ctx) ctx->err = buf;
     g_last_error = buf;
+    (void)cudaGetLastError();   // a handled failure (e.g. out of memory) must not leak into the next call
     return code;
 }
 

@@ -55,11 +55,13 @@ int sdfs_set_error(sdfs_ctx *ctx, int code, const char *fmt, ...);
 #define CUDA_TRY(ctx, expr)                                                             \
     do {                                                                                \
         cudaError_t _e = (expr);                                                        \
-        if (_e != cudaSuccess)                                                          \
+        if (_e != cudaSuccess) {                                                        \
+            (void)cudaGetLastError(); /* clear the non-sticky error for later calls */  \
             return sdfs_set_error((ctx), _e == cudaErrorMemoryAllocation ? SDFS_ERR_NOMEM \
                                                                          : SDFS_ERR_CUDA, \
                                   "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,         \
                                   cudaGetErrorString(_e));                              \
+        }                                                                               \
     } while (0)
 
 #define ARG_CHECK(ctx, cond)                                                            \
