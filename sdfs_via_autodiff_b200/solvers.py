@@ -20,6 +20,20 @@ default_max_iter = int(1e6)
 
 KRYLOV = {"bicgstab": 0, "gmres": 1}
 
+_NOT_AN_OPERATOR = ("{} needs an operator of this package (WCOperator, or a closure over T_ssy/T_gcy such as "
+                    "`lambda w: T_ssy(w, shapes, params, arrays)`): the loop runs inside a CUDA kernel; there is "
+                    "no host-side iteration of arbitrary Python callables and no CPU fallback")
+
+
+def _report(history, current_iter, max_iter, verbose, print_skip, stride=1):
+    """Print what the reference's loop prints (solvers.py:37-46) from the device-side history:
+    history[i // stride] is the error of iteration i for i % stride == 0."""
+    if verbose and history is not None:
+        for i in range(0, current_iter, print_skip):
+            if i % stride == 0 and i // stride < len(history):
+                print("iter = {}, error = {}".format(i, history[i // stride]))
+    _finish_messages(current_iter, max_iter, verbose)
+
 
 def _finish_messages(current_iter, max_iter, verbose):
     if current_iter == max_iter:
@@ -32,12 +46,11 @@ def successive_approx(f, x_init, tol=default_tolerance, max_iter=default_max_ite
                       verbose=True, print_skip=1000, return_info=False):
     "Uses successive approximation on f."
     op = resolve_operator(f)
+    if op is None:
+        raise TypeError(_NOT_AN_OPERATOR.format("successive_approx"))
     max_iter = int(max_iter)
     if verbose:
         print("Beginning iteration\n\n")
-    if op is None:
-        out = _host_driven_sa(f, x_init, tol, max_iter, verbose, print_skip)
-        return out
     ctx = op.ctx
     w0 = op._in(x_init)
     w_out = ctx.empty(op.shapes)
@@ -50,32 +63,10 @@ def successive_approx(f, x_init, tol=default_tolerance, max_iter=default_max_ite
     check(lib.sdfs_solve_sa(op.handle, w0.ptr, float(tol), max_iter, w_out.ptr, C.byref(iters), C.byref(ferr),
                             hist.ptr if hist is not None else None, int(max(1, print_skip)), cap), ctx.handle)
     k = iters.value
-    if verbose:
-        h = hist.numpy()
-        for i in range(0, k, print_skip):
-            if i // print_skip < cap:
-                print("iter = {}, error = {}".format(i, h[i // print_skip]))
-    _finish_messages(k, max_iter, verbose)
+    _report(hist.numpy() if verbose else None, k, max_iter, verbose, print_skip, stride=max(1, print_skip))
     if return_info:
         return w_out, k, dict(final_error=ferr.value)
     return w_out, k
-
-
-def _host_driven_sa(f, x_init, tol, max_iter, verbose, print_skip):
-    """Generic ``f`` (any Python callable): the reference loop verbatim, one call of
-    ``f`` per iteration.  ``f`` itself decides where it computes."""
-    current_iter = 0
-    x = x_init
-    error = tol + 1
-    while error > tol and current_iter < max_iter:
-        x_new = f(x)
-        error = float(np.max(np.abs(np.asarray(x_new) - np.asarray(x))))
-        if verbose and current_iter % print_skip == 0:
-            print("iter = {}, error = {}".format(current_iter, error))
-        current_iter += 1
-        x = x_new
-    _finish_messages(current_iter, max_iter, verbose)
-    return x, current_iter
 
 
 def newton_solver(f, x_init, tol=default_tolerance, max_iter=default_max_iter,
@@ -91,9 +82,7 @@ def newton_solver(f, x_init, tol=default_tolerance, max_iter=default_max_iter,
     the reference's choice) or restarted GMRES (``krylov="gmres"``)."""
     op = resolve_operator(f)
     if op is None:
-        raise TypeError("newton_solver needs an operator of this package (WCOperator, or a closure over "
-                        "T_ssy/T_gcy): the Jacobian-vector product is analytic, there is no autodiff "
-                        "of arbitrary Python callables and no CPU fallback")
+        raise TypeError(_NOT_AN_OPERATOR.format("newton_solver"))
     max_iter = int(max_iter)
     if verbose:
         print("Beginning iteration\n\n")
@@ -109,10 +98,7 @@ def newton_solver(f, x_init, tol=default_tolerance, max_iter=default_max_iter,
                                 int(krylov_maxiter) if krylov_maxiter else 0, w_out.ptr, C.byref(outer),
                                 C.byref(ferr), h_err, h_inner, cap, C.byref(nmv)), ctx.handle)
     k = outer.value
-    if verbose:
-        for i in range(0, min(k, cap), print_skip):
-            print("iter = {}, error = {}".format(i, h_err[i]))
-    _finish_messages(k, max_iter, verbose)
+    _report(list(h_err[:min(k, cap)]) if verbose else None, k, max_iter, verbose, print_skip, stride=1)
     if return_info:
         n = min(k, cap)
         return w_out, k, dict(final_error=ferr.value, errors=list(h_err[:n]),
