@@ -340,6 +340,28 @@ def test_sweep_batched_T_and_solve():
     assert info["gemms"] > 0 and (info["inner_total"] > 0).all()
 
 
+def test_sweep_gcy_columns():
+    """The sweep works for the GCY model as well (6-D state, same shared-P structure)."""
+    shapes = (2, 3, 2, 3, 2, 3)
+    base = O.GCY()
+    arrays = O.discretize_gcy(base, shapes)
+    prefs = np.array([[13.01, 1.5, 0.9987], [9.0, 1.8, 0.998], [11.0, 1.4, 0.9985]])
+    op = S.make_sweep_operator(S.GCY(), shapes)
+    rng = np.random.default_rng(3)
+    W = 300 + 400 * rng.random((3,) + shapes)
+    got = np.asarray(S.sweep_apply_T(op, prefs, W))
+    for b, (γ, ψ, β) in enumerate(prefs):
+        m = O.GCY(γ=γ, ψ=ψ, β=β)
+        np.testing.assert_allclose(got[b], O.KronGCY(shapes, m.params, arrays).T(W[b]), rtol=RTOL_T)
+    Wd, iters, errs = S.sweep_solve(op, prefs, algorithm="newton", tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12)
+    for b, (γ, ψ, β) in enumerate(prefs):
+        m = O.GCY(γ=γ, ψ=ψ, β=β)
+        kop = O.KronGCY(shapes, m.params, arrays)
+        w_ref, _ = O.newton_solver(kop.T, np.full(shapes, 800.0), jvp=kop.jvp, bicgstab_atol=1e-11, verbose=False)
+        w_ref, _ = O.successive_approx(kop.T, w_ref, tol=1e-11, verbose=False)
+        np.testing.assert_allclose(np.asarray(Wd)[b], w_ref, rtol=RTOL_W)
+
+
 def test_error_behaviour_and_pinned_buffers():
     ctx = S.Context.default()
     # dense P that cannot fit: a clear out-of-memory error, not a crash (8.8 TB at 10^6 states)
