@@ -96,6 +96,100 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32, 1) k_sa_small(SmallArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// N <= 128: register-resident P.  512 threads; 4 lanes per row, 8 rows per warp; lane l4 of a
+// row holds the 32 matrix entries of columns {8k + 2 l4, 8k + 2 l4 + 1}, k = 0..15, in
+// registers for the whole solve, so an iteration's mat-vec is 16 broadcast LDS.128 of x, 32
+// DFMA and 2 shuffle stages per lane.  Measured B200 latencies (tools/lat_probe.cu: pow 844
+// cycles for one warp but 2116 when 32 warps issue it, warp_sum(f64) ~200, __syncthreads
+// ~75) drive the rest: the transcendental epilogue runs only in the first N threads (4 full
+// warps, exp/log form), the sup-norm uses two REDUX.MAX on the high/low words of |dy|
+// instead of five 64-bit shuffle stages, and the four warp maxima meet in shared memory.
+// Two __syncthreads per iteration.
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) k_sa_small_reg(SmallArgs a) {
+    __shared__ __align__(16) double sx[2][128];
+    __shared__ double ss[128];
+    __shared__ unsigned long long smax[2][4];
+    const int N = a.N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int l4 = lane & 3;
+    const int row = warp * 8 + (lane >> 2);
+    const bool row_ok = row < N;
+    double2 pr[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int c = 8 * k + 2 * l4;
+        pr[k].x = (row_ok && c < N) ? a.P[(int64_t)row * a.ld + c] : 0.0;
+        pr[k].y = (row_ok && c + 1 < N) ? a.P[(int64_t)row * a.ld + c + 1] : 0.0;
+    }
+    const double theta = a.theta, beta = a.beta, inv_theta = 1.0 / a.theta;
+    const bool owner = tid < N;
+    double w_mine = 0.0, ar = 0.0, ac = 0.0;
+    if (tid < 128) { sx[0][tid] = 0.0; sx[1][tid] = 0.0; }
+    if (tid < 8) smax[tid >> 2][tid & 3] = 0ull;
+    __syncthreads();
+    if (owner) {
+        w_mine = a.w_init[tid];
+        ar = a.a_row[tid];
+        ac = a.a_col[tid];
+        sx[0][tid] = ac * pow(w_mine, theta);
+    }
+    __syncthreads();
+    long long it = 0;
+    double error = a.tol + 1.0;
+    while (error > a.tol && it < a.max_iter) {
+        const int cur = (int)(it & 1), nxt = cur ^ 1;
+        const double *x = sx[cur];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+            const double2 x0 = *reinterpret_cast<const double2 *>(x + 8 * k + 2 * l4);
+            const double2 x1 = *reinterpret_cast<const double2 *>(x + 8 * (k + 1) + 2 * l4);
+            a0 = fma(pr[k].x, x0.x, a0);
+            a1 = fma(pr[k].y, x0.y, a1);
+            a2 = fma(pr[k + 1].x, x1.x, a2);
+            a3 = fma(pr[k + 1].y, x1.y, a3);
+        }
+        double s = (a0 + a1) + (a2 + a3);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (l4 == 0 && row_ok) ss[row] = s;
+        __syncthreads();
+        if (warp < 4) {
+            double d = 0.0;
+            if (owner) {
+                const double y = 1.0 + beta * pw<MODE>(ar * ss[tid], inv_theta);
+                d = fabs(y - w_mine);
+                w_mine = y;
+                sx[nxt][tid] = ac * pw<MODE>(y, theta);
+            }
+            // NaN-propagating max of non-negative doubles through their bit patterns
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+            const int hi = (int)(bits >> 32);
+            const int mhi = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned lo = (hi == mhi) ? (unsigned)bits : 0u;
+            const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
+            if (lane == 0) smax[cur][warp] = ((unsigned long long)(unsigned)mhi << 32) | mlo;
+        }
+        __syncthreads();
+        unsigned long long m = smax[cur][0];
+        m = max(m, smax[cur][1]);
+        m = max(m, smax[cur][2]);
+        m = max(m, smax[cur][3]);
+        error = __longlong_as_double((long long)m);
+        if (tid == 0 && a.err_hist && (it % a.hist_stride) == 0 && (it / a.hist_stride) < a.hist_cap)
+            a.err_hist[it / a.hist_stride] = error;
+        ++it;
+    }
+    if (owner) a.w_out[tid] = w_mine;
+    if (tid == 0) {
+        *a.iters_out = it;
+        *a.final_err_out = error;
+    }
+}
+
 // returns 1 if the small path handled the solve, 0 if not applicable, <0 on error
 int small_sa_try(sdfs_op *op, const double *d_w_init, double tol, int64_t max_iter, double *d_w_out,
                  double *d_err_hist, int64_t hist_stride, int64_t hist_cap) {
@@ -121,6 +215,18 @@ int small_sa_try(sdfs_op *op, const double *d_w_init, double tol, int64_t max_it
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_sa_small<W, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_sa_small<W, M><<<1, W * 32, smem, ctx->stream>>>(a);                                               \
     } while (0)
+    if (N <= 128 && (variant == 321 || variant == 1)) {          // default: register-resident P
+        k_sa_small_reg<1><<<1, 512, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+        return 1;
+    }
+    if (N <= 128 && variant == 0) {                              // register-resident P, pow()
+        k_sa_small_reg<0><<<1, 512, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+        return 1;
+    }
     switch (variant) {
         case 320: LAUNCH_SMALL(32, 0); break;
         case 80: LAUNCH_SMALL(8, 0); break;
