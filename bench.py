@@ -274,10 +274,21 @@ def run_ours(args, shapes):
         ctx.sync()
         dt = max_over_ranks(time.perf_counter() - t0)
         res = float(np.max(np.abs(np.asarray(op(ws)) - np.asarray(ws))))
-        solve = {"algo": "newton+bicgstab(device)", "tol": 1e-8, "seconds": dt, "outer_iters": int(k),
-                 "inner_iters": [int(x) for x in info["inner_iters"]], "operator_applications": int(info["matvecs"]),
-                 "max_abs_Tw_minus_w": res,
+        solve = {"algo": "newton+bicgstab(device), reference stopping rule (inner atol 1e-4)", "tol": 1e-8, "seconds": dt,
+                 "outer_iters": int(k), "inner_iters": [int(x) for x in info["inner_iters"]],
+                 "operator_applications": int(info["matvecs"]), "max_abs_Tw_minus_w": res,
                  "apps_per_s": info["matvecs"] / dt}
+        # the reference's rule stops when BiCGSTAB returns its zero start (||Tw-w||_2 <= 1e-4); a solve that
+        # really reaches max|Tw-w| <= 1e-8 needs a tighter inner tolerance:
+        barrier()
+        t0 = time.perf_counter()
+        wt, kt, it_ = S.newton_solver(op, w0, tol=1e-8, bicgstab_atol=1e-9, krylov_rtol=1e-10, verbose=False,
+                                      return_info=True)
+        ctx.sync()
+        dtt = max_over_ranks(time.perf_counter() - t0)
+        rest = float(np.max(np.abs(np.asarray(op(wt)) - np.asarray(wt))))
+        solve["tight"] = {"inner_atol": 1e-9, "inner_rtol": 1e-10, "seconds": dtt, "outer_iters": int(kt),
+                          "operator_applications": int(it_["matvecs"]), "max_abs_Tw_minus_w": rest}
 
     extra = {}
     if world == 1:

@@ -115,7 +115,6 @@ int comm_allgather_rows(sdfs_ctx *ctx, double *d_vec, int64_t N) {
 }
 
 size_t arena_bytes_for(int64_t maxN);                 // loops.cu
-void arena_view(void *base, int64_t maxN, ArenaView *v);
 
 extern "C" {
 

@@ -20,14 +20,6 @@ namespace cg = cooperative_groups;
 
 struct sdfs_comm_state;                // comm.cu
 
-// Peer-visible exchange arena (one per rank, mapped by all peers through CUDA IPC).
-// Layout: [flags | partial slots | xin ping | xin pong]
-struct ArenaView {
-    unsigned long long *flags;         // SDFS_MAX_RANKS monotonically increasing arrival counters
-    double *slots;                     // [SDFS_MAX_RANKS][NSLOT_SETS][SDFS_MAX_GRID] partial reductions
-    double *xin[2];                    // matvec input vectors (full length, padded)
-};
-
 struct sdfs_ctx {
     int device = 0;
     int sm_count = 0;

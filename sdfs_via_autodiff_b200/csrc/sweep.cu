@@ -310,28 +310,6 @@ static int sweep_step(sdfs_op *op, SweepWork &w, int64_t B, const double *Win, d
     return sweep_gemm(op, w, B, w.V, ep, sc);
 }
 
-#if 0
-static int sweep_step_old(sdfs_op *op, SweepWork &w, int64_t B, const double *Win, double *Wout, bool track) {
-    sdfs_ctx *ctx = op->ctx;
-    const int64_t N = op->dv.N;
-    SweepCols sc{w.gamma, w.theta, w.beta, track ? w.done : nullptr};
-    const int64_t tot = N * B;
-    const int tiles_m = (int)((N + GM - 1) / GM), tiles_b = (int)((B + GN - 1) / GN);
-    const size_t smem = (size_t)GSTAGES * (GM + GN) * GS * sizeof(double);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
-    if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
-    k_sweep_gemm<<<tiles_m * tiles_b, GTHREADS, smem, ctx->stream>>>(op->dv.P, N, op->dv.ld, w.V, B, w.ldw, w.sc, w.mz, Win,
-                                                                     Wout, sc, track ? w.err_bits : nullptr, tiles_b);
-    if (prof) {
-        CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
-        ctx->prof_used += 2;
-    }
-    ctx->launches += 2;
-    CUDA_TRY(ctx, cudaGetLastError());
-    return SDFS_OK;
-}
-#endif
 
 __global__ void k_fill_panel(double *W, int64_t N, int64_t B, int64_t ldw, double v) {
     const int64_t tot = N * B;

@@ -168,6 +168,15 @@ if "c5" in which:
     steps = int(iters.max())
     r["solve_B64"] = dict(seconds=dt, max_iters=steps, min_iters=int(iters.min()),
                           ms_per_step=dt / steps * 1e3, tflops=2.0 * N * N * 64 * steps / dt / 1e12)
+    for B in (512, 4096):
+        t0 = time.perf_counter()
+        Wd2, it2, er2, info = S.sweep_solve(op, lattice[:B], algorithm="newton", return_info=True)
+        ctx.sync()
+        dt2 = time.perf_counter() - t0
+        r[f"newton_solve_B{B}"] = dict(seconds=dt2, gemms=int(info["gemms"]), outer_min=int(it2.min()), outer_max=int(it2.max()),
+                                       inner_total_max=int(info["inner_total"].max()),
+                                       tflops=2.0 * N * N * B * info["gemms"] / dt2 / 1e12,
+                                       any_nan=bool(np.isnan(np.asarray(Wd2)).any()))
     # spot-check two columns against single-column device solves
     for j in (0, 63):
         m = S.SSY(γ=prefs[j, 0], ψ=prefs[j, 1], β=prefs[j, 2])
