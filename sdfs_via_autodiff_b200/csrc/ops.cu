@@ -200,11 +200,14 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
             const bool last_vec = (pass == nx - 1);
             for (int m = 0; m < kv.n_modes; ++m) {
                 const bool last_mode = (m == kv.n_modes - 1);
+                // few fibres (small grids): narrower CTAs give more work items to spread over the SMs
+                const int64_t fibres = N / kv.shape[kv.modes[m].dim];
+                const int threads = fibres >= (int64_t)ctx->sm_count * 512 ? 256 : (fibres >= (int64_t)ctx->sm_count * 128 ? 128 : 64);
                 if (last_mode && last_vec) {
-                    k_kron_last<<<grid, 256, 0, ctx->stream>>>(kv, m, in, s0_done, e);
+                    k_kron_last<<<grid, threads, 0, ctx->stream>>>(kv, m, in, s0_done, e);
                 } else {
                     double *out = last_mode ? (op->work + 2 * op->ldv) : op->kron_tmp[m & 1];
-                    k_kron_mode<<<grid, 256, 0, ctx->stream>>>(kv, m, in, out);
+                    k_kron_mode<<<grid, threads, 0, ctx->stream>>>(kv, m, in, out);
                     in = out;
                     if (last_mode) s0_done = out;
                 }
