@@ -85,6 +85,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // Barrier across every CTA of every rank.  Returns false (uniformly) after a peer
 // timeout so the kernel can unwind instead of hanging the GPU.
 __device__ __forceinline__ bool all_sync(cg::grid_group &grid, const LoopEnv &env, unsigned long long &epoch) {
+    // writer side of the generic -> async proxy hand-over: the matvec input stored by this thread
+    // is read by the TMA unit (async proxy) of other CTAs after this barrier
+    asm volatile("fence.proxy.async;" ::: "memory");
     if (env.nranks == 1) {
         grid.sync();
         return true;

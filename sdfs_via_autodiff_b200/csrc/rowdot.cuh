@@ -396,9 +396,10 @@ __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const
         }
         __syncthreads();                        // previous item's matrix no longer in use
         const double *msrc = md.mat + (long long)mat * n * n;
-        for (int e = threadIdx.x; e < n * NMAX; e += blockDim.x) {
+        const int n4 = (n + 3) & ~3;            // rows padded to a multiple of 4 (zero rows)
+        for (int e = threadIdx.x; e < n4 * NMAX; e += blockDim.x) {
             const int i = e / NMAX, j = e - i * NMAX;
-            smat[e] = (j < n) ? msrc[i * n + j] : 0.0;
+            smat[e] = (i < n && j < n) ? msrc[i * n + j] : 0.0;
         }
         __syncthreads();
         const long long f = chunk * blockDim.x + threadIdx.x;
@@ -412,16 +413,23 @@ __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const
             double x[NMAX];
 #pragma unroll
             for (int j = 0; j < NMAX; ++j) x[j] = (j < n) ? in[base + j * md.stride] : 0.0;
-            for (int i = 0; i < n; ++i) {
-                const double2 *row = reinterpret_cast<const double2 *>(smat + i * NMAX);
-                double a0 = 0.0, a1 = 0.0;
+            // four output rows at a time: eight independent FMA chains hide the fp64 latency
+            for (int i = 0; i < n; i += 4) {
+                const double2 *r0 = reinterpret_cast<const double2 *>(smat + i * NMAX);
+                const double2 *r1 = r0 + NMAX / 2, *r2 = r1 + NMAX / 2, *r3 = r2 + NMAX / 2;
+                double a[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
                 for (int j = 0; j < NMAX / 2; ++j) {
-                    const double2 mv = row[j];
-                    a0 = fma(mv.x, x[2 * j], a0);
-                    a1 = fma(mv.y, x[2 * j + 1], a1);
+                    const double2 m0 = r0[j], m1 = r1[j], m2 = r2[j], m3 = r3[j];
+                    const double xa = x[2 * j], xb = x[2 * j + 1];
+                    a[0][0] = fma(m0.x, xa, a[0][0]); a[0][1] = fma(m0.y, xb, a[0][1]);
+                    a[1][0] = fma(m1.x, xa, a[1][0]); a[1][1] = fma(m1.y, xb, a[1][1]);
+                    a[2][0] = fma(m2.x, xa, a[2][0]); a[2][1] = fma(m2.y, xb, a[2][1]);
+                    a[3][0] = fma(m3.x, xa, a[3][0]); a[3][1] = fma(m3.y, xb, a[3][1]);
                 }
-                sink(base + i * md.stride, a0 + a1);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (i + r < n) sink(base + (i + r) * md.stride, a[r][0] + a[r][1]);
             }
         }
     }
