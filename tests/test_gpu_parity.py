@@ -433,5 +433,25 @@ def test_full_size_properties(model, shapes):
     qk, ek = k.sdf(w)
     np.testing.assert_allclose(np.asarray(qd), np.asarray(qk), rtol=1e-11)
     np.testing.assert_allclose(np.asarray(ed), np.asarray(ek), rtol=1e-9, atol=1e-11)
-    # small-grid oracle anchor for the same code path is in the tests above
+    # direct oracle parity at full size (the oracle's factored form needs no dense P)
+    if model == "ssy":
+        ref_model = O.SSY()
+        kop = O.KronSSY(shapes, ref_model.params, O.discretize_ssy(ref_model, shapes))
+    else:
+        ref_model = O.GCY()
+        kop = O.KronGCY(shapes, ref_model.params, O.discretize_gcy(ref_model, shapes))
+    np.testing.assert_allclose(np.asarray(d(w)), kop.T(w), rtol=RTOL_T)
+    np.testing.assert_allclose(np.asarray(d.jvp(w, v)), kop.jvp(w, v), rtol=1e-10, atol=1e-11)
+    # BASELINE.md anchors: Newton outer iteration counts and the range of w*
+    wk, kk, info = S.newton_solver(k, np.full(shapes, 800.0), verbose=False, return_info=True)
+    wkn = np.asarray(wk)
+    if model == "ssy":
+        assert abs(kk - 9) <= 1                       # "SSY Newton, (18,)*4: 9 outer"
+    else:
+        assert abs(kk - 7) <= 1                       # "GCY Newton (7,)*6: 7 outer", w* in [272.74, 492.84]
+        np.testing.assert_allclose([wkn.min(), wkn.max()], [272.74, 492.84], rtol=2e-5)
+    assert info["errors"][-1] == 0.0 and info["inner_iters"][-1] == 0
+    # the factor-form solution is a fixed point of the streamed dense operator as well
+    assert np.linalg.norm(np.asarray(d(wk)) - wkn) <= 1.05e-4
+    assert np.linalg.norm(kop.T(wkn) - wkn) <= 1.05e-4
     del d, k
