@@ -103,6 +103,12 @@ int sdfs_factors_count(sdfs_factors *f, int *n_arrays);
 /* element count and device pointer of the idx-th array of the reference tuple */
 int sdfs_factors_array(sdfs_factors *f, int idx, int64_t *n_elems, const double **d_ptr);
 
+/* Log-linear closed form of the W/C ratio (wc_loglinear, ssy_model.py:143-153 /
+ * gcy_model.py:146-157) evaluated at every grid state: h_coeffs[7] =
+ * (A0, A_hlam, A_hc, A_hz, A_z, A_hzpi, A_zpi) (last two ignored for SSY);
+ * d_out[n] = exp(value) if exponentiate else value.  Warm start for the solvers. */
+int sdfs_factors_loglinear(sdfs_factors *f, const double *h_coeffs, int exponentiate, double *d_out);
+
 /* ---- operators ----------------------------------------------------------
  * Dense single-index form (ssy/discrete/temp_ssy.py:49-106 P_x, :116-148 H,
  * :153-159 single_index_T).  d_P is row-major with leading dimension ld >= N

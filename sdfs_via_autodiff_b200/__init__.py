@@ -17,3 +17,4 @@ from .solvers import (successive_approx, newton_solver, solver, solvers,        
                       default_tolerance, default_max_iter)
 from .sdf import solve_ssy, solve_gcy, SDFResult                 # noqa: F401
 from .sweep import make_sweep_operator, sweep_apply_T, sweep_solve                      # noqa: F401
+from .loglinear import loglinear_guess                                               # noqa: F401

@@ -61,6 +61,7 @@ _SIGS = {
     "sdfs_factors_destroy": (C.c_int, [c_vp]),
     "sdfs_factors_count": (C.c_int, [c_vp, P(C.c_int)]),
     "sdfs_factors_array": (C.c_int, [c_vp, C.c_int, P(c_i64), P(c_vp)]),
+    "sdfs_factors_loglinear": (C.c_int, [c_vp, P(c_f64), C.c_int, c_vp]),
     "sdfs_op_from_dense": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_f64, c_f64, P(c_vp)]),
     "sdfs_op_from_factors": (C.c_int, [c_vp, c_vp, C.c_int, P(c_vp)]),
     "sdfs_op_destroy": (C.c_int, [c_vp]),

@@ -406,6 +406,55 @@ __global__ void __launch_bounds__(256) k_expand_dense(KronView kv, int64_t row_b
     }
 }
 
+// wc_loglinear on the grid (ssy_model.py:143-153, gcy_model.py:146-157)
+__global__ void k_loglinear(int model, KronView kv, const double *__restrict__ h_lam, const double *__restrict__ h_c,
+                            const double *__restrict__ h_z, const double *__restrict__ z, const double *__restrict__ h_zpi,
+                            const double *__restrict__ zpi, double phi_c, double phi_z, double phi_zpi, double A0,
+                            double Al, double Ac, double Ahz, double Az, double Ahzpi, double Azpi, int exponentiate,
+                            double *__restrict__ out) {
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < kv.N; n += (int64_t)gridDim.x * blockDim.x) {
+        int c[SDFS_MAX_DIMS];
+        int64_t rem = n;
+        for (int d = kv.D - 1; d >= 0; --d) { c[d] = (int)(rem % kv.shape[d]); rem /= kv.shape[d]; }
+        double v;
+        if (model == SDFS_MODEL_SSY) {          // (l,k,i,j)
+            const double sz = h_z[c[2]] * 2.0 * (phi_z * phi_z) + phi_z * phi_z;
+            const double sc = h_c[c[1]] * 2.0 * (phi_c * phi_c) + phi_c * phi_c;
+            v = A0 + Al * h_lam[c[0]] + Ac * sc + Ahz * sz + Az * z[c[2] * kv.shape[3] + c[3]];
+        } else {                                 // (z,zpi,hz,hc,hzpi,hlam)
+            const double sz = h_z[c[2]] * 2.0 * (phi_z * phi_z) + phi_z * phi_z;
+            const double sc = h_c[c[3]] * 2.0 * (phi_c * phi_c) + phi_c * phi_c;
+            const double sp = h_zpi[c[4]] * 2.0 * (phi_zpi * phi_zpi) + phi_zpi * phi_zpi;
+            const double zz = z[((c[1] * kv.shape[2] + c[2]) * kv.shape[4] + c[4]) * kv.shape[0] + c[0]];
+            const double zp = zpi[c[4] * kv.shape[1] + c[1]];
+            v = A0 + Al * h_lam[c[5]] + Ac * sc + Ahz * sz + Az * zz + Ahzpi * sp + Azpi * zp;
+        }
+        out[n] = exponentiate ? exp(v) : v;
+    }
+}
+
+extern "C" int sdfs_factors_loglinear(sdfs_factors *f, const double *h_coeffs, int exponentiate, double *d_out) {
+    if (!f) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_factors_loglinear: NULL");
+    sdfs_ctx *ctx = f->ctx;
+    ARG_CHECK(ctx, h_coeffs && d_out);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    KronView kv;
+    factors_to_kron(f, &kv);
+    const double *pr = f->params;
+    const int grid = (int)((kv.N + 255) / 256 < 4096 ? (kv.N + 255) / 256 : 4096);
+    if (f->model == SDFS_MODEL_SSY)
+        k_loglinear<<<grid, 256, 0, ctx->stream>>>(f->model, kv, f->d_arr[0], f->d_arr[2], f->d_arr[4], f->d_arr[6], nullptr, nullptr,
+                                                   pr[6], pr[5], 0.0, h_coeffs[0], h_coeffs[1], h_coeffs[2], h_coeffs[3], h_coeffs[4],
+                                                   0.0, 0.0, exponentiate, d_out);
+    else
+        k_loglinear<<<grid, 256, 0, ctx->stream>>>(f->model, kv, f->d_arr[13], f->d_arr[7], f->d_arr[4], f->d_arr[0], f->d_arr[10],
+                                                   f->d_arr[2], pr[6], pr[9], pr[15], h_coeffs[0], h_coeffs[1], h_coeffs[2],
+                                                   h_coeffs[3], h_coeffs[4], h_coeffs[5], h_coeffs[6], exponentiate, d_out);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SDFS_OK;
+}
+
 int launch_build_scalings(sdfs_ctx *ctx, const sdfs_factors *f, const KronView &kv, double gamma,
                           double theta, double mu_c, double *a_row, double *a_col, double *e_sdf) {
     const double *h_lam = (f->model == SDFS_MODEL_SSY) ? f->d_arr[0] : f->d_arr[13];

@@ -22,3 +22,10 @@ class GCY:
         self.ρ_ππ, self.φ_zπ, self.ρ_zπ, self.s_zπ = ρ_ππ, φ_zπ, ρ_zπ, s_zπ
         self.params = (β, ψ, γ, ρ_λ, s_λ, μ_c, φ_c, ρ, ρ_π, φ_z, ρ_c, s_c, ρ_z, s_z,
                        ρ_ππ, φ_zπ, ρ_zπ, s_zπ)
+
+
+def wc_loglinear_factory(gcy):
+    """Constant terms of the log-linear approximation of the W/C ratio and a function that
+    evaluates it (log w) at a state (h_λ, h_c, h_z, h_zπ, z, z_π) -- mirror of gcy_model.py:80-159."""
+    from .loglinear import gcy_factory
+    return gcy_factory(gcy)

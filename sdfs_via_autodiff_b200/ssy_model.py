@@ -21,3 +21,10 @@ class SSY:
         self.s_z, self.s_c, self.s_λ = s_z, s_c, s_λ
         self.θ = (1 - γ) / (1 - 1 / ψ)
         self.params = β, γ, ψ, μ_c, ρ, ϕ_z, ϕ_c, ρ_z, ρ_c, ρ_λ, s_z, s_c, s_λ
+
+
+def wc_loglinear_factory(ssy):
+    """Constant terms of the log-linear approximation of the W/C ratio and a function that
+    evaluates it (log w) at a state (h_λ, h_c, h_z, z) -- mirror of ssy_model.py:86-156."""
+    from .loglinear import ssy_factory
+    return ssy_factory(ssy)

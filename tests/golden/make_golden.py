@@ -99,6 +99,19 @@ def main():
               open(os.path.join(HERE, "reference_facts.json"), "w"), indent=1)
     print("facts done", trace)
 
+    # log-linear closed form (ssy_model.py:86-156, gcy_model.py:80-159), evaluated by the reference itself
+    rng = np.random.default_rng(99)
+    ll = {}
+    for tag, mod, cls, kw, dim in (("ssy", ssy_m, ssy_m.SSY, {}, 4), ("ssy_alt", ssy_m, ssy_m.SSY, {"γ": 10.0, "ψ": 1.5, "β": 0.998}, 4),
+                                   ("gcy", gcy_m, gcy_m.GCY, {}, 6), ("gcy_alt", gcy_m, gcy_m.GCY, {"γ": 9.0, "ψ": 1.8, "β": 0.998}, 6)):
+        model = cls(**kw)
+        f = mod.wc_loglinear_factory(model)
+        pts = (rng.standard_normal((12, dim)) * ([0.01, 0.3, 0.3, 0.002] if dim == 4 else [0.01, 0.3, 0.3, 0.3, 0.002, 0.002])).tolist()
+        pts.append([0.0] * dim)
+        ll[tag] = {"kwargs": kw, "points": pts, "values": [float(f(tuple(x))) for x in pts]}
+    json.dump(ll, open(os.path.join(HERE, "loglinear.json"), "w"), indent=1)
+    print("loglinear done", ll["ssy"]["values"][-1], ll["gcy"]["values"][-1])
+
 
 if __name__ == "__main__":
     main()

@@ -82,3 +82,16 @@ def test_solver_front_end_semantics(capsys):
                    "Iteration converged after 5 iterations\n")
     sv._report(None, 7, 7, False, 1000)
     assert capsys.readouterr().out == "Warning: Hit maximum iteration number 7\n"
+
+
+def test_host_loglinear_factory_matches_reference_golden(golden_dir):
+    """Host mirror of wc_loglinear_factory (own root finder instead of scipy.brentq): agrees with
+    the values produced by the reference files to brentq's own tolerance (xtol 2e-12)."""
+    from sdfs_via_autodiff_b200.ssy_model import wc_loglinear_factory as ssy_ll
+    from sdfs_via_autodiff_b200.gcy_model import wc_loglinear_factory as gcy_ll
+    g = json.load(open(os.path.join(golden_dir, "loglinear.json")))
+    for tag, rec in g.items():
+        f = ssy_ll(S.SSY(**rec["kwargs"])) if tag.startswith("ssy") else gcy_ll(S.GCY(**rec["kwargs"]))
+        got = [f(tuple(x)) for x in rec["points"]]
+        np.testing.assert_allclose(got, rec["values"], rtol=1e-9)
+        assert set(f.coeffs) >= {"A0", "Ah_λ", "Ah_c", "Ah_z", "Az", "qbar"}

@@ -362,6 +362,26 @@ def test_sweep_gcy_columns():
         np.testing.assert_allclose(np.asarray(Wd)[b], w_ref, rtol=RTOL_W)
 
 
+def test_loglinear_guess_on_device_and_warm_start():
+    from oracle.loglinear import loglinear_grid_ssy, loglinear_grid_gcy
+    shapes = (4, 5, 6, 7)
+    ref = loglinear_grid_ssy(O.SSY(), shapes, O.discretize_ssy(O.SSY(), shapes))
+    np.testing.assert_allclose(np.asarray(S.loglinear_guess(S.SSY(), shapes, log=True)), ref, rtol=1e-9)
+    np.testing.assert_allclose(np.asarray(S.loglinear_guess(S.SSY(), shapes)), np.exp(ref), rtol=1e-9)
+    gshapes = (2, 3, 4, 3, 2, 3)
+    gref = loglinear_grid_gcy(O.GCY(), gshapes, O.discretize_gcy(O.GCY(), gshapes))
+    np.testing.assert_allclose(np.asarray(S.loglinear_guess(S.GCY(), gshapes, log=True)), gref, rtol=1e-9)
+    # warm start: Newton from the closed form needs no more outer iterations than from w0 = 800
+    shapes = (10, 10, 10, 10)
+    op = S.make_T_ssy(S.SSY(), shapes, storage="kron")
+    w_cold, k_cold = S.newton_solver(op, np.full(shapes, 800.0), tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12,
+                                     verbose=False)
+    w_warm, k_warm = S.newton_solver(op, S.loglinear_guess(S.SSY(), shapes), tol=1e-9, bicgstab_atol=1e-10,
+                                     krylov_rtol=1e-12, verbose=False)
+    assert k_warm <= k_cold
+    np.testing.assert_allclose(np.asarray(w_warm), np.asarray(w_cold), rtol=RTOL_W)
+
+
 def test_error_behaviour_and_pinned_buffers():
     ctx = S.Context.default()
     # dense P that cannot fit: a clear out-of-memory error, not a crash (8.8 TB at 10^6 states)

@@ -194,3 +194,17 @@ def test_gcy_newton_and_sdf_euler_identity():
     rows = np.array([0, 17, 728])
     M = O.sdf_rows(w, P, ac, e_sdf_gcy(shapes, gcy.params, arrays), β, θ, rows)
     np.testing.assert_allclose((P[rows] * M).sum(1), q_f[rows], rtol=1e-12)
+
+
+def test_loglinear_matches_reference_golden(golden_dir):
+    """wc_loglinear_factory of the reference (ssy_model.py:86-156, gcy_model.py:80-159), evaluated
+    by the importable reference files themselves (tests/golden/make_golden.py)."""
+    from oracle.loglinear import loglinear_ssy, loglinear_gcy
+    g = json.load(open(os.path.join(golden_dir, "loglinear.json")))
+    for tag, rec in g.items():
+        if tag.startswith("ssy"):
+            f = loglinear_ssy(O.SSY(**rec["kwargs"]))
+        else:
+            f = loglinear_gcy(O.GCY(**rec["kwargs"]))
+        got = [f(tuple(x)) for x in rec["points"]]
+        np.testing.assert_allclose(got, rec["values"], rtol=1e-13)
