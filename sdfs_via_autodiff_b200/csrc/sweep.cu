@@ -228,7 +228,10 @@ struct SweepWork {
     void free_all() {
         void *ps[] = {hl, sc, mz, gamma, theta, beta, last_err, err_bits, iters, done, n_active, V, Wa, Wb};
         for (void *p : ps) if (p) cudaFree(p);
+        hl = sc = mz = gamma = theta = beta = last_err = V = Wa = Wb = nullptr;
+        err_bits = nullptr; iters = nullptr; done = n_active = nullptr;
     }
+    ~SweepWork() { free_all(); }     // error paths return early: nothing may leak
 };
 
 static int sweep_setup(sdfs_op *op, const double *h_prefs, int64_t B, bool panels, SweepWork *w) {
