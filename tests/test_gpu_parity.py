@@ -184,6 +184,60 @@ def test_successive_approx_edge_semantics():
         op(np.ones(7))
 
 
+def _trace(out):
+    """(iteration, error) pairs and the remaining lines of a solver's stdout."""
+    pairs, rest = [], []
+    for line in out.splitlines():
+        if line.startswith("iter = "):
+            a, b = line.split(", error = ")
+            pairs.append((int(a[len("iter = "):]), float(b)))
+        elif line.strip():
+            rest.append(line)
+    return pairs, rest
+
+
+def test_printed_output_matches_reference_style(capsys):
+    """Same stdout as the reference loop (solvers.py:28-46): header, 'iter = k, error = e' every
+    print_skip iterations, closing message -- rebuilt from the device-side history."""
+    ssy = O.SSY()
+    shapes = (3, 4, 5, 6)
+    arrays = O.discretize_ssy(ssy, shapes)
+    kop = O.KronSSY(shapes, ssy.params, arrays)
+    op = S.make_T_ssy(ssy, shapes, arrays)
+    for kwargs in (dict(print_skip=1000), dict(print_skip=7, tol=1e-4), dict(print_skip=1, tol=1e-2),
+                   dict(print_skip=50, tol=0.0, max_iter=120)):
+        capsys.readouterr()
+        w_ref, k_ref = O.successive_approx(kop.T, np.full(shapes, 800.0), verbose=True, **kwargs)
+        ref_pairs, ref_rest = _trace(capsys.readouterr().out)
+        w, k = S.successive_approx(op, np.full(shapes, 800.0), verbose=True, **kwargs)
+        pairs, rest = _trace(capsys.readouterr().out)
+        assert k == k_ref and rest == ref_rest
+        assert [p[0] for p in pairs] == [p[0] for p in ref_pairs]
+        np.testing.assert_allclose([p[1] for p in pairs], [p[1] for p in ref_pairs], rtol=1e-6)
+    # Newton prints every outer iteration (print_skip = 1) and ends on the exact-zero step
+    capsys.readouterr()
+    w_ref, k_ref = O.newton_solver(kop.T, np.full(shapes, 800.0), jvp=kop.jvp, verbose=True)
+    ref_pairs, ref_rest = _trace(capsys.readouterr().out)
+    w, k = S.newton_solver(op, np.full(shapes, 800.0), verbose=True)
+    pairs, rest = _trace(capsys.readouterr().out)
+    assert abs(k - k_ref) <= 1 and pairs[-1][1] == 0.0 and ref_pairs[-1][1] == 0.0
+    assert rest[0] == ref_rest[0] == "Beginning iteration"
+    assert rest[-1] == f"Iteration converged after {k} iterations"
+    np.testing.assert_allclose([p[1] for p in pairs[:2]], [p[1] for p in ref_pairs[:2]], rtol=1e-4)
+    # max_iter semantics of the Newton outer loop
+    capsys.readouterr()
+    w2, k2 = S.newton_solver(op, np.full(shapes, 800.0), max_iter=2, verbose=False)
+    assert k2 == 2 and "Warning: Hit maximum iteration number 2" in capsys.readouterr().out
+    # reference quirk: from a negative start T gives NaN, BiCGSTAB never iterates (NaN > atol2 is
+    # False), so x - 0 = x, the step size is exactly 0 and the loop reports convergence at once
+    w3, k3 = S.newton_solver(op, np.full(shapes, -5.0), verbose=False)
+    with np.errstate(all="ignore"):
+        w3_ref, k3_ref = O.newton_solver(kop.T, np.full(shapes, -5.0), jvp=kop.jvp, verbose=False)
+    assert k3 == k3_ref == 1
+    np.testing.assert_array_equal(np.asarray(w3), w3_ref)
+    assert (w3_ref == -5.0).all()
+
+
 def test_newton_sandpit_trace_and_parity(golden_dir):
     """BiCGSTAB parity mode on the grid of the reference's recorded run."""
     facts = json.load(open(os.path.join(golden_dir, "reference_facts.json")))
