@@ -176,6 +176,15 @@ int sdfs_solve_newton(sdfs_op *op, const double *d_w_init, double tol, int64_t m
                       double *final_err, double *h_outer_err, int64_t *h_inner_iters,
                       int64_t cap, int64_t *total_matvecs);
 
+/* anderson_solver (solvers.py:98-124, a jaxopt.AndersonAcceleration wrapper with history_size=10,
+ * mixing_frequency=4, beta=8.0, ridge=1e-6).  jaxopt is not vendored: its update rule is restated
+ * (parity unpinned): history of the last m iterates/residuals, alpha from the ridge-regularised
+ * bordered Gram system, extrapolation sum alpha_i (x_i + beta r_i) once the history is full and on
+ * every mixing_frequency-th iteration, x <- T x otherwise; stops when ||T x - x||_2 <= tol. */
+int sdfs_solve_anderson(sdfs_op *op, const double *d_w_init, double tol, int64_t max_iter,
+                        int history_size, int mixing_frequency, double beta, double ridge,
+                        double *d_w_out, int64_t *iters, double *final_err);
+
 /* ---- batched (gamma, psi, beta) sweep -----------------------------------
  * B parameter columns share one P (P does not depend on preferences); each
  * step is S = P V (fp64 tensor-core GEMM) with per-column prologue/epilogue.

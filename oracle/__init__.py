@@ -29,5 +29,5 @@ from .operators import (T_ssy_loops, T_gcy_loops, T_ssy, T_gcy,  # noqa: F401
                         dense_ssy, dense_gcy, dense_T, dense_jvp,
                         KronSSY, KronGCY)
 from .solvers import (successive_approx, newton_solver, solver,  # noqa: F401
-                      bicgstab_jax, gmres_restarted, solvers)
+                      bicgstab_jax, gmres_restarted, solvers, anderson_solver)
 from .sdf import sdf_dense, sdf_rows                             # noqa: F401

@@ -172,7 +172,52 @@ def newton_solver(f, x_init, tol=default_tolerance, max_iter=default_max_iter,
                              history=history)
 
 
-solvers = dict(newton=newton_solver, successive_approx=successive_approx)
+def anderson_solver(f, x_init, tol=default_tolerance, max_iter=10000, verbose=True, history_size=10,
+                    mixing_frequency=4, beta=8.0, ridge=1e-6):
+    """Anderson acceleration as configured at solvers.py:98-124 (jaxopt.AndersonAcceleration with
+    history_size=10, mixing_frequency=4, beta=8.0, ridge=1e-6).  PARITY UNPINNED: jaxopt is an
+    un-vendored, un-pinned dependency that cannot be installed here; this restates its published
+    update rule -- history of the last m iterates x_i and residuals r_i = f(x_i) - x_i, Gram matrix
+    G_ij = <r_i, r_j>, alpha from [[0, 1^T], [1, G + ridge I]] [nu; alpha] = e_0, extrapolation
+    sum_i alpha_i (x_i + beta r_i) once the history is full and on every mixing_frequency-th
+    iteration, plain x <- f(x) otherwise; error = ||r||_2; stop when error <= tol."""
+    shape = np.shape(x_init)
+    x = np.asarray(x_init, dtype=np.float64).reshape(-1).copy()
+    m, n = history_size, x.size
+    X = np.tile(x, (m, 1))
+    R = np.zeros((m, n))
+    G = np.zeros((m, m))
+    k, err = 0, np.inf
+    while err > tol and k < max_iter:
+        pos = k % m
+        fx = np.asarray(f(x.reshape(shape))).reshape(-1)
+        r = fx - x
+        X[pos], R[pos] = x, r
+        row = R @ r
+        G[pos, :] = row
+        G[:, pos] = row
+        if k >= m and k % mixing_frequency == 0:
+            H = np.zeros((m + 1, m + 1))
+            H[0, 1:] = 1.0
+            H[1:, 0] = 1.0
+            H[1:, 1:] = G + ridge * np.eye(m)
+            e0 = np.zeros(m + 1)
+            e0[0] = 1.0
+            alpha = np.linalg.solve(H, e0)[1:]
+            x_new = alpha @ X + beta * (alpha @ R)
+        else:
+            x_new = fx
+        err = float(np.linalg.norm(r))
+        x = x_new
+        k += 1
+    if k == max_iter:
+        print(f"Warning: Hit maximum iteration number {max_iter}")
+    elif verbose:
+        print(f"Iteration converged after {k} iterations")
+    return x.reshape(shape), k
+
+
+solvers = dict(newton=newton_solver, successive_approx=successive_approx, anderson=anderson_solver)
 
 
 def solver(f, x_init, algorithm="newton", verbose=True):

@@ -78,6 +78,7 @@ _SIGS = {
     "sdfs_solve_sa": (C.c_int, [c_vp, c_vp, c_f64, c_i64, c_vp, P(c_i64), P(c_f64), c_vp, c_i64, c_i64]),
     "sdfs_solve_newton": (C.c_int, [c_vp, c_vp, c_f64, c_i64, C.c_int, c_f64, c_f64, C.c_int, c_i64, c_vp,
                                     P(c_i64), P(c_f64), P(c_f64), P(c_i64), c_i64, P(c_i64)]),
+    "sdfs_solve_anderson": (C.c_int, [c_vp, c_vp, c_f64, c_i64, C.c_int, C.c_int, c_f64, c_f64, c_vp, P(c_i64), P(c_f64)]),
     "sdfs_sweep_solve_sa": (C.c_int, [c_vp, P(c_f64), c_i64, c_f64, c_f64, c_i64, c_vp, P(c_i64), P(c_f64)]),
     "sdfs_sweep_solve_newton": (C.c_int, [c_vp, P(c_f64), c_i64, c_f64, c_f64, c_i64, c_f64, c_f64, c_i64, c_vp,
                                           P(c_i64), P(c_f64), P(c_i64), P(c_i64)]),

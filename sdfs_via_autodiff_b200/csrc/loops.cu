@@ -661,6 +661,146 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_newton_loop(co
 }
 
 // ---------------------------------------------------------------------------
+// Anderson acceleration (solvers.py:98-124: jaxopt.AndersonAcceleration, history 10, mixing
+// frequency 4, beta 8, ridge 1e-6).  jaxopt is un-vendored: the update rule is restated
+// (oracle/solvers.py::anderson_solver) -- parity unpinned.
+// ---------------------------------------------------------------------------
+#define AND_MAX_HIST 16
+struct AndersonArgs {
+    const double *w_init;
+    double *w_out;
+    double *x, *fx;        // current iterate and f(x) (own rows)
+    double *X, *R;         // histories: m vectors of ldv doubles each
+    long long ldv;
+    double tol;
+    long long max_iter;
+    int m, mix;
+    double beta_mix, ridge;
+};
+
+// Solve the (m+1)x(m+1) system [[0,1^T],[1,G+ridge I]] [nu;alpha] = e0 (partial pivoting).
+__device__ __forceinline__ void anderson_alphas(const double *G, int m, double ridge, double *alpha /* m */) {
+    double H[(AND_MAX_HIST + 1) * (AND_MAX_HIST + 2)];
+    const int n = m + 1, ldh = n + 1;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= n; ++j) H[i * ldh + j] = 0.0;
+    for (int j = 1; j < n; ++j) { H[j] = 1.0; H[j * ldh] = 1.0; }
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) H[(i + 1) * ldh + j + 1] = G[i * AND_MAX_HIST + j] + (i == j ? ridge : 0.0);
+    H[n] = 1.0;    // right-hand side e0
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        double best = fabs(H[c * ldh + c]);
+        for (int r = c + 1; r < n; ++r)
+            if (fabs(H[r * ldh + c]) > best) { best = fabs(H[r * ldh + c]); piv = r; }
+        if (piv != c)
+            for (int j = 0; j <= n; ++j) { const double t = H[c * ldh + j]; H[c * ldh + j] = H[piv * ldh + j]; H[piv * ldh + j] = t; }
+        const double d = H[c * ldh + c];
+        for (int r = c + 1; r < n; ++r) {
+            const double fct = H[r * ldh + c] / d;
+            for (int j = c; j <= n; ++j) H[r * ldh + j] -= fct * H[c * ldh + j];
+        }
+    }
+    double sol[AND_MAX_HIST + 1];
+    for (int r = n - 1; r >= 0; --r) {
+        double acc = H[r * ldh + n];
+        for (int j = r + 1; j < n; ++j) acc -= H[r * ldh + j] * sol[j];
+        sol[r] = acc / H[r * ldh + r];
+    }
+    for (int i = 0; i < m; ++i) alpha[i] = sol[i + 1];
+}
+
+template <class Op>
+__global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_anderson_loop(const __grid_constant__ Op op, AndersonArgs a, LoopEnv env) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    __shared__ double smem[SDFS_WARPS * NVAL + NVAL];
+    __shared__ double sG[AND_MAX_HIST * AND_MAX_HIST];
+    __shared__ double sAlpha[AND_MAX_HIST];
+    Scratch sc;
+    sc.rp = reinterpret_cast<RowPipe<1> *>(dyn_smem);
+    sc.smat = reinterpret_cast<double *>(dyn_smem);
+    op.init(sc);
+    unsigned long long epoch = env.epoch0;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rb = op.row_begin(), re = op.row_end();
+    const double theta = op.theta(), beta = op.beta(), inv_theta = 1.0 / op.theta();
+    const double *a_row = op.a_row(), *a_col = op.a_col();
+    const int m = a.m;
+    for (int e = threadIdx.x; e < AND_MAX_HIST * AND_MAX_HIST; e += blockDim.x) sG[e] = 0.0;
+    // x = x0 ; history tiled with x0 (jaxopt init_state), residual history zero ; xin = a_col x^theta
+    for (int64_t n = rb + tid; n < re; n += nth) {
+        const double w0 = a.w_init[n];
+        a.x[n] = w0;
+        for (int i = 0; i < m; ++i) { a.X[i * a.ldv + n] = w0; a.R[i * a.ldv + n] = 0.0; }
+        store_all_ranks(env, 0, n, a_col[n] * pow(w0, theta));
+    }
+    if (!all_sync(grid, env, epoch)) return;
+    long long k = 0;
+    double error = INFINITY;
+    while (error > a.tol && k < a.max_iter) {
+        const int pos = (int)(k % m);
+        // f(x), residual, history update
+        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double s) {
+                const double y = 1.0 + beta * pow(a_row[n] * s, inv_theta);
+                const double xn = a.x[n];
+                a.fx[n] = y;
+                a.X[pos * a.ldv + n] = xn;
+                a.R[pos * a.ldv + n] = y - xn;
+            })) return;
+        if (!all_sync(grid, env, epoch)) return;
+        // new Gram row: <R_i, r>, i = 0..m-1 (8 per barrier)
+        for (int i0 = 0; i0 < m; i0 += NVAL) {
+            const int nb = (m - i0) < NVAL ? (m - i0) : NVAL;
+            double hv[NVAL];
+#pragma unroll
+            for (int b = 0; b < NVAL; ++b) hv[b] = 0.0;
+            const double *rcur = a.R + pos * a.ldv;
+            for (int64_t n = rb + tid; n < re; n += nth) {
+                const double rn = rcur[n];
+#pragma unroll
+                for (int b = 0; b < NVAL; ++b)
+                    if (b < nb) hv[b] += a.R[(i0 + b) * a.ldv + n] * rn;
+            }
+            if (!grid_allreduce<NVAL, false>(grid, env, epoch, (i0 / NVAL) & 1 ? SET_X : SET_Y, hv, smem)) return;
+            if (threadIdx.x == 0)
+#pragma unroll
+                for (int b = 0; b < NVAL; ++b)
+                    if (b < nb) { sG[pos * AND_MAX_HIST + i0 + b] = hv[b]; sG[(i0 + b) * AND_MAX_HIST + pos] = hv[b]; }
+        }
+        __syncthreads();
+        error = sqrt(sG[pos * AND_MAX_HIST + pos]);
+        const bool extrapolate = (k >= m) && (k % a.mix == 0);
+        if (extrapolate && threadIdx.x == 0) anderson_alphas(sG, m, a.ridge, sAlpha);
+        __syncthreads();
+        for (int64_t n = rb + tid; n < re; n += nth) {
+            double xn;
+            if (extrapolate) {
+                double pa = 0.0, ra = 0.0;
+                for (int i = 0; i < m; ++i) {
+                    pa += sAlpha[i] * a.X[i * a.ldv + n];
+                    ra += sAlpha[i] * a.R[i * a.ldv + n];
+                }
+                xn = pa + a.beta_mix * ra;
+            } else {
+                xn = a.fx[n];
+            }
+            a.x[n] = xn;
+            store_all_ranks(env, 0, n, a_col[n] * pow(xn, theta));
+        }
+        if (!all_sync(grid, env, epoch)) return;
+        ++k;
+    }
+    for (int64_t n = rb + tid; n < re; n += nth) a.w_out[n] = a.x[n];
+    if (tid == 0) {
+        env.status->iters = k;
+        env.status->final_err = error;
+        env.status->epoch_end = epoch;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
 static int build_env(sdfs_op *op, LoopEnv *env) {
@@ -787,6 +927,57 @@ int sdfs_solve_sa(sdfs_op *op, const double *d_w_init, double tol, int64_t max_i
     if (env.nranks > 1) {
         *comm_epoch(ctx) = hs->epoch_end;   // every rank passed the same barriers
         TRY(comm_allgather_rows(ctx, d_w_out, op->dv.N));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (iters) *iters = hs->iters;
+    if (final_err) *final_err = hs->final_err;
+    return SDFS_OK;
+}
+
+int sdfs_solve_anderson(sdfs_op *op, const double *d_w_init, double tol, int64_t max_iter, int history_size,
+                        int mixing_frequency, double beta, double ridge, double *d_w_out, int64_t *iters,
+                        double *final_err) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_solve_anderson: NULL op");
+    sdfs_ctx *ctx = op->ctx;
+    ARG_CHECK(ctx, d_w_init && d_w_out && max_iter >= 0);
+    ARG_CHECK(ctx, history_size >= 2 && history_size <= AND_MAX_HIST && mixing_frequency >= 1);
+    if (!ctx->coop_supported) return sdfs_set_error(ctx, SDFS_ERR_UNSUPPORTED, "device lacks cooperative launch");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool dense = op->storage == SDFS_STORAGE_DENSE;
+    const int64_t N = dense ? op->dv.N : op->kv.N;
+    TRY(op_ensure_work(op, 16 + 2 * AND_MAX_HIST));
+    LoopEnv env;
+    TRY(build_env(op, &env));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(LoopStatus), ctx->stream));
+    AndersonArgs a{};
+    const int64_t ld = op->ldv;
+    a.w_init = d_w_init; a.w_out = d_w_out;
+    a.x = op->work + 2 * ld; a.fx = op->work + 3 * ld;
+    a.X = op->work + 16 * ld; a.R = op->work + (16 + AND_MAX_HIST) * ld;
+    a.ldv = ld; a.tol = tol; a.max_iter = max_iter; a.m = history_size; a.mix = mixing_frequency;
+    a.beta_mix = beta; a.ridge = ridge;
+    int grid = 0;
+    if (dense) {
+        DenseLoopOp lop{op->dv};
+        TRY(coop_grid(ctx, k_anderson_loop<DenseLoopOp>, lop.dyn_smem(), 1, dense_groups(op->dv), env.nranks > 1, &grid));
+        void *args[] = {&lop, &a, &env};
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_anderson_loop<DenseLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, lop.dyn_smem(), ctx->stream));
+    } else {
+        if (!op->kron_tmp[0]) {
+            CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[0], (size_t)N * sizeof(double)));
+            CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)N * sizeof(double)));
+        }
+        KronLoopOp lop{op->kv, op->kron_tmp[0], op->kron_tmp[1]};
+        TRY(coop_grid(ctx, k_anderson_loop<KronLoopOp>, lop.dyn_smem(), 2, (N + SDFS_THREADS - 1) / SDFS_THREADS, false, &grid));
+        void *args[] = {&lop, &a, &env};
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_anderson_loop<KronLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, lop.dyn_smem(), ctx->stream));
+    }
+    ctx->launches++;
+    LoopStatus *hs = (LoopStatus *)ctx->h_status;
+    TRY(finish_loop(ctx, hs, 0));
+    if (env.nranks > 1) {
+        *comm_epoch(ctx) = hs->epoch_end;
+        TRY(comm_allgather_rows(ctx, d_w_out, N));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (iters) *iters = hs->iters;

@@ -106,9 +106,26 @@ def newton_solver(f, x_init, tol=default_tolerance, max_iter=default_max_iter,
     return w_out, k
 
 
-def anderson_solver(f, x_init, tol=default_tolerance, max_iter=10000, verbose=True):
-    raise NotImplementedError("anderson_solver (jaxopt wrapper, solvers.py:98-124) is outside the "
-                              "accelerated hot path; use 'newton' or 'successive_approx'")
+def anderson_solver(f, x_init, tol=default_tolerance, max_iter=10000, verbose=True, return_info=False):
+    """Anderson acceleration with the reference's hard-coded parameters (solvers.py:98-124:
+    history_size=10, mixing_frequency=4, beta=8.0, ridge=1e-6), device resident.  jaxopt is not
+    vendored with the reference, so its update rule is restated (see include/sdfs_b200.h):
+    results agree with the package's oracle, parity with jaxopt itself is unpinned."""
+    op = resolve_operator(f)
+    if op is None:
+        raise TypeError(_NOT_AN_OPERATOR.format("anderson_solver"))
+    max_iter = int(max_iter)
+    ctx = op.ctx
+    w0 = op._in(x_init)
+    w_out = ctx.empty(op.shapes)
+    iters, ferr = C.c_int64(), C.c_double()
+    check(lib.sdfs_solve_anderson(op.handle, w0.ptr, float(tol), max_iter, 10, 4, 8.0, 1e-6, w_out.ptr,
+                                  C.byref(iters), C.byref(ferr)), ctx.handle)
+    current_iter = iters.value
+    _finish_messages(current_iter, max_iter, verbose)
+    if return_info:
+        return w_out, current_iter, dict(final_error=ferr.value)
+    return w_out, current_iter
 
 
 def fixed_point_via_gradient_decent(f, x_init):

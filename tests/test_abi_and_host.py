@@ -71,8 +71,10 @@ def test_solver_front_end_semantics(capsys):
         S.solver(f, np.array([0.0]), algorithm="no-such-algo")
     out = capsys.readouterr().out
     assert "Algorithm no-such-algo not found." in out and "Falling back to successive approximation." in out
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError, match="no CPU fallback"):
         S.solvers["anderson"](f, np.array([0.0]))
+    with pytest.raises(NotImplementedError):
+        S.solvers["gd"](f, np.array([0.0]))
     assert S.default_tolerance == 1e-7 and S.default_max_iter == 1000000
     # the printed trace is rebuilt from the device-side history exactly as the reference prints it
     hist = [1.0, 0.25, 0.0625]                      # errors of iterations 0, 2, 4 (print_skip = 2)

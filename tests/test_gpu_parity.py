@@ -416,6 +416,31 @@ def test_sweep_gcy_columns():
         np.testing.assert_allclose(np.asarray(Wd)[b], w_ref, rtol=RTOL_W)
 
 
+@pytest.mark.parametrize("storage", ["dense", "kron"])
+def test_anderson_solver_device(storage, capsys):
+    """solvers['anderson'] (solvers.py:98-124 parameters) against the package oracle's restatement."""
+    ssy = O.SSY()
+    for shapes in ((2, 3, 4, 5), (5, 6, 7, 8)):
+        arrays = O.discretize_ssy(ssy, shapes)
+        kop = O.KronSSY(shapes, ssy.params, arrays)
+        op = S.make_T_ssy(ssy, shapes, arrays, storage=storage)
+        w_ref, k_ref = O.anderson_solver(kop.T, np.full(shapes, 800.0), verbose=False)
+        w, k, info = S.anderson_solver(op, np.full(shapes, 800.0), verbose=False, return_info=True)
+        wn = np.asarray(w)
+        assert info["final_error"] <= 1e-7 and np.linalg.norm(kop.T(wn) - wn) <= 1.5e-7
+        # the small bordered Gram systems are ill-conditioned near convergence, so the two
+        # implementations may part ways by a few mixing periods, not more
+        assert abs(k - k_ref) <= max(40, 0.05 * k_ref), (k, k_ref)
+        np.testing.assert_allclose(wn, w_ref, rtol=1e-7)
+    capsys.readouterr()
+    T = lambda w: S.T_ssy(w, shapes, ssy.params, arrays, storage=storage)
+    w2 = S.solver(T, np.full(shapes, 800.0), algorithm="anderson")
+    assert "Iteration converged after" in capsys.readouterr().out
+    np.testing.assert_allclose(np.asarray(w2), wn, rtol=1e-12)
+    w3, k3 = S.anderson_solver(op, np.full(shapes, 800.0), max_iter=13, verbose=False)
+    assert k3 == 13 and "Warning: Hit maximum iteration number 13" in capsys.readouterr().out
+
+
 def test_loglinear_guess_on_device_and_warm_start():
     from oracle.loglinear import loglinear_grid_ssy, loglinear_grid_gcy
     shapes = (4, 5, 6, 7)

@@ -208,3 +208,15 @@ def test_loglinear_matches_reference_golden(golden_dir):
             f = loglinear_gcy(O.GCY(**rec["kwargs"]))
         got = [f(tuple(x)) for x in rec["points"]]
         np.testing.assert_allclose(got, rec["values"], rtol=1e-13)
+
+
+def test_anderson_oracle_converges_to_the_fixed_point():
+    """Anderson with the reference's parameters (parity with jaxopt itself is unpinned)."""
+    ssy = O.SSY()
+    shapes = (2, 3, 4, 5)
+    op = O.KronSSY(shapes, ssy.params, O.discretize_ssy(ssy, shapes))
+    w, k = O.anderson_solver(op.T, np.full(shapes, 800.0), verbose=False)
+    w_sa, k_sa = O.successive_approx(op.T, np.full(shapes, 800.0), tol=1e-9, verbose=False)
+    assert k < 10428                                 # fewer operator applications than plain iteration
+    assert np.linalg.norm(op.T(w) - w) <= 1.5e-7
+    np.testing.assert_allclose(w, w_sa, rtol=1e-7)
