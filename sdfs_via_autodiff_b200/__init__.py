@@ -13,7 +13,7 @@ from .gcy_model import GCY                                       # noqa: F401
 from .operator import WCOperator, Factors                        # noqa: F401
 from .ssy_wc_ratio import discretize_ssy, T_ssy, make_T_ssy, test_compute_wc_ratio_ssy   # noqa: F401
 from .gcy_wc_ratio import discretize_gcy, T_gcy, make_T_gcy, test_compute_wc_ratio_gcy   # noqa: F401
-from .solvers import (successive_approx, newton_solver, solver, solvers,                 # noqa: F401
+from .solvers import (successive_approx, newton_solver, anderson_solver, solver, solvers,                 # noqa: F401
                       default_tolerance, default_max_iter)
 from .sdf import solve_ssy, solve_gcy, SDFResult                 # noqa: F401
 from .sweep import make_sweep_operator, sweep_apply_T, sweep_solve                      # noqa: F401
