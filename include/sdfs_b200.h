@@ -44,7 +44,7 @@ typedef struct sdfs_factors sdfs_factors; /* discretised model: Markov factor ar
 
 enum { SDFS_MODEL_SSY = 0, SDFS_MODEL_GCY = 1 };
 enum { SDFS_KRYLOV_BICGSTAB = 0, SDFS_KRYLOV_GMRES = 1 };
-enum { SDFS_STORAGE_DENSE = 0, SDFS_STORAGE_KRON = 1, SDFS_STORAGE_DENSE_REPLICATED = 2 };
+enum { SDFS_STORAGE_DENSE = 0, SDFS_STORAGE_KRON = 1, SDFS_STORAGE_DENSE_REPLICATED = 2, SDFS_STORAGE_CONTINUOUS = 3 };
 
 /* ---- context ---------------------------------------------------------- */
 int sdfs_abi_version(void);
@@ -123,6 +123,16 @@ int sdfs_op_from_dense(sdfs_ctx *ctx, const double *d_P, int64_t N, int64_t ld,
  * each rank materialises only its row slice; SDFS_STORAGE_DENSE_REPLICATED keeps the
  * full P on every rank (parameter sweeps shard columns, not rows). */
 int sdfs_op_from_factors(sdfs_ctx *ctx, sdfs_factors *f, int storage, sdfs_op **out);
+/* Continuous-state operator ("next" row of the scope table): the T of
+ * ssy/continuous_junnan/ssy_wc_ratio_continuous.py:125-226 and
+ * gcy/continuous/gcy_wc_ratio_continuous.py -- conditional expectation by a shock rule (Gauss-Hermite
+ * nodes/weights, or Monte-Carlo draws with weights 1/Q) and multilinear interpolation of w on uniform
+ * grids (utils.py:6-23).  h_grids: the D grids concatenated (D = 4 SSY: h_lam,h_c,h_z,z; D = 6 GCY:
+ * h_lam,h_c,h_z,h_zpi,z,z_pi); h_nodes: D x Q row-major; h_weights: Q.  The returned handle works
+ * with sdfs_op_apply_T / _jvp and the three solvers. */
+int sdfs_op_continuous(sdfs_ctx *ctx, int model, const double *h_params, const int32_t *h_sizes,
+                       const double *h_grids, const double *h_nodes, const double *h_weights,
+                       int64_t Q, sdfs_op **out);
 int sdfs_op_destroy(sdfs_op *op);
 int sdfs_op_info(sdfs_op *op, int64_t *N, int64_t *ld, int64_t *row_begin,
                  int64_t *row_end, double *beta, double *theta, int *storage);

@@ -1,0 +1,138 @@
+"""Continuous-state wealth-consumption operators -- host mirror of
+/root/reference/code/ssy/continuous_junnan/ssy_wc_ratio_continuous.py and
+/root/reference/code/gcy/continuous/gcy_wc_ratio_continuous.py (build_grid, T_fun_factory,
+wc_ratio_continuous).  The conditional expectation uses Gauss-Hermite quadrature (the
+reference's quantecon.quad.qnwnorm([d]*dim), restated with numpy's hermgauss) or Monte-Carlo
+draws; w is interpolated multilinearly on uniform grids (utils.py:6-23).  All arithmetic runs in
+libsdfs_b200 (csrc/cont.cuh); the solvers are the same device-resident loops as for the
+discretised models.  Parity with the JAX original is unpinned (jax/quantecon not installable,
+no recorded outputs); the package oracle restates it independently (oracle/continuous.py).
+"""
+import ctypes as C
+import itertools
+
+import numpy as np
+from numpy.polynomial.hermite import hermgauss
+
+from ._lib import lib, check
+from .device import Context
+from .operator import WCOperator, MODEL_SSY, MODEL_GCY
+from . import solvers as _sv          # module (the package attribute `solvers` is the dict)
+
+
+def _is_gcy(model):
+    return hasattr(model, "ρ_ππ")
+
+
+def build_grid(model, *sizes, num_std_devs=3.2):
+    """Interpolation grids: SSY (h_λ, h_c, h_z, z) sizes, GCY (h_λ, h_c, h_z, h_zπ, z, z_π) sizes."""
+    if len(sizes) == 1 and hasattr(sizes[0], "__len__"):
+        sizes = tuple(sizes[0])
+    if _is_gcy(model):
+        (β, ψ, γ, ρ_λ, s_λ, μ_c, φ_c, ρ, ρ_π, φ_z, ρ_c, s_c, ρ_z, s_z, ρ_ππ, φ_zπ, ρ_zπ, s_zπ) = model.params
+        grids = []
+        for s, r, n in zip((s_λ, s_c, s_z, s_zπ), (ρ_λ, ρ_c, ρ_z, ρ_zπ), sizes[:4]):
+            g_max = num_std_devs * np.sqrt(s ** 2 / (1 - r ** 2))
+            grids.append(np.linspace(-g_max, g_max, n))
+        h_zπ_max = num_std_devs * np.sqrt(s_zπ ** 2 / (1 - ρ_zπ ** 2))
+        σ_zπ_max = φ_zπ * np.exp(h_zπ_max)
+        zπ_max = num_std_devs * np.sqrt(σ_zπ_max ** 2 / (1 - ρ_ππ ** 2))
+        zπ_grid = np.linspace(-zπ_max, zπ_max, sizes[5])
+        h_z_max = num_std_devs * np.sqrt(s_z ** 2 / (1 - ρ_z ** 2))
+        σ_z_max = φ_z * np.exp(h_z_max)
+        z_max = (ρ_π * zπ_grid[-1] + num_std_devs * σ_z_max) / (1 - ρ)
+        z_min = (ρ_π * zπ_grid[0] - num_std_devs * σ_z_max) / (1 - ρ)
+        grids += [np.linspace(z_min, z_max, sizes[4]), zπ_grid]
+        return tuple(grids)
+    β, γ, ψ, μ_c, ρ, ϕ_z, ϕ_c, ρ_z, ρ_c, ρ_λ, s_z, s_c, s_λ = model.params
+    grids = []
+    for s, r, n in zip((s_λ, s_c, s_z), (ρ_λ, ρ_c, ρ_z), sizes[:3]):
+        g_max = num_std_devs * np.sqrt(s ** 2 / (1 - r ** 2))
+        grids.append(np.linspace(-g_max, g_max, n))
+    h_z_max = num_std_devs * np.sqrt(s_z ** 2 / (1 - ρ_z ** 2))
+    z_max = num_std_devs * ϕ_z * np.exp(h_z_max)
+    grids.append(np.linspace(-z_max, z_max, sizes[3]))
+    return tuple(grids)
+
+
+def gauss_hermite_normal(d, dim):
+    """Nodes (dim, d**dim) and weights of the tensor-product Gauss-Hermite rule for N(0, I)
+    (what quantecon.quad.qnwnorm([d]*dim) returns, first dimension varying fastest)."""
+    x, w = hermgauss(d)
+    x, w = x * np.sqrt(2.0), w / np.sqrt(np.pi)
+    idx = np.array(list(itertools.product(range(d), repeat=dim)))[:, ::-1]      # first dimension fastest
+    return np.ascontiguousarray(x[idx].T), np.prod(w[idx], axis=1)
+
+
+def T_fun_factory(params, method="quadrature", batch_size=None, model_kind=None, ctx=None):
+    """Operator T for the continuous-state model.  ``params`` as in the reference:
+    (model_params, grids, nodes, weights) for "quadrature", (model_params, grids, mc_draws) for
+    "monte_carlo" (nodes / mc_draws of shape (dim, Q)).  ``batch_size`` is accepted and ignored:
+    the kernel needs no batching."""
+    ctx = ctx or Context.default()
+    if method == "quadrature":
+        model_params, grids, nodes, weights = params
+    elif method == "monte_carlo":
+        model_params, grids, nodes = params
+        nodes = np.asarray(nodes, dtype=np.float64)
+        weights = np.full(nodes.shape[1], 1.0 / nodes.shape[1])               # jnp.mean
+    else:
+        raise KeyError("Method not found.")
+    grids = [np.ascontiguousarray(np.asarray(g, dtype=np.float64)) for g in grids]
+    dim = len(grids)
+    kind = model_kind if model_kind is not None else (MODEL_SSY if dim == 4 else MODEL_GCY)
+    nodes = np.ascontiguousarray(np.asarray(nodes, dtype=np.float64))
+    weights = np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
+    if nodes.shape != (dim, weights.size):
+        raise ValueError(f"nodes must have shape ({dim}, Q), got {nodes.shape}")
+    sizes = (C.c_int32 * dim)(*[g.size for g in grids])
+    flat = np.ascontiguousarray(np.concatenate(grids))
+    p = (C.c_double * len(model_params))(*[float(v) for v in model_params])
+    h = C.c_void_p()
+    dp = C.POINTER(C.c_double)
+    check(lib.sdfs_op_continuous(ctx.handle, kind, p, sizes, flat.ctypes.data_as(dp), nodes.ctypes.data_as(dp),
+                                 weights.ctypes.data_as(dp), weights.size, C.byref(h)), ctx.handle)
+    return WCOperator(ctx, h, tuple(g.size for g in grids))
+
+
+def make_T_continuous(model, sizes, method="quadrature", d=5, mc_draws=None, mc_draw_size=2000, seed=1234,
+                      num_std_devs=3.2, ctx=None):
+    grids = build_grid(model, *sizes, num_std_devs=num_std_devs)
+    dim = len(grids)
+    if method == "quadrature":
+        nodes, weights = gauss_hermite_normal(d, dim)
+        params = (model.params, grids, nodes, weights)
+    elif method == "monte_carlo":
+        if mc_draws is None:      # the reference draws with jax.random.PRNGKey(seed); NumPy's generator here
+            mc_draws = np.random.default_rng(seed).standard_normal((dim, mc_draw_size))
+        params = (model.params, grids, mc_draws)
+    else:
+        raise KeyError("Approximation method not found.")
+    return grids, T_fun_factory(params, method, model_kind=MODEL_GCY if _is_gcy(model) else MODEL_SSY, ctx=ctx)
+
+
+def wc_ratio_continuous(model, *grid_sizes, num_std_devs=3.2, d=5, mc_draw_size=2000, seed=1234, w_init=None,
+                        ram_free=20, tol=1e-5, method="quadrature", algorithm="successive_approx", verbose=True,
+                        write_to_file=False, filename="w_star_data.npy", mc_draws=None):
+    """Iterate to convergence on the continuous-state operator and return (grids, w_star).
+    Same keywords as the reference (grid sizes default to 10,10,10,20 for SSY and 10,10,10,10,20,20
+    for GCY; w_init defaults to ones).  ``ram_free`` is accepted for compatibility (no batching is
+    needed); ``tol`` is forwarded to the solver (the reference accepts it but never forwards it);
+    ``write_to_file`` defaults to False here (the reference's two consecutive np.save records are
+    written when it is True)."""
+    if not grid_sizes:
+        grid_sizes = (10, 10, 10, 10, 20, 20) if _is_gcy(model) else (10, 10, 10, 20)
+    grids, T = make_T_continuous(model, grid_sizes, method, d, mc_draws, mc_draw_size, seed, num_std_devs)
+    if w_init is None:
+        w_init = T.ctx.full(T.shapes, 1.0)
+    try:
+        fn = _sv.solvers[algorithm]
+    except KeyError:
+        print(f"Algorithm {algorithm} not found.  \nFalling back to successive approximation.\n")
+        fn = _sv.successive_approx
+    w_star, _ = fn(T, w_init, tol=tol, verbose=verbose)
+    if write_to_file:
+        with open(filename, "wb") as f:
+            np.save(f, np.array(grids, dtype=object), allow_pickle=True)
+            np.save(f, np.asarray(w_star))
+    return grids, w_star

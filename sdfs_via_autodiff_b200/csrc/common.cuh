@@ -104,6 +104,22 @@ struct KronView {
     double beta, theta;
 };
 
+// Continuous-state operator (ssy/continuous_junnan/ssy_wc_ratio_continuous.py,
+// gcy/continuous/gcy_wc_ratio_continuous.py): uniform interpolation grids, shock nodes/weights.
+#define SDFS_STORAGE_CONT 3
+struct ContView {
+    int model, D, Q;
+    int n[SDFS_MAX_DIMS];
+    const double *grid[SDFS_MAX_DIMS];   // device: grid values per axis
+    double g0[SDFS_MAX_DIMS], intv[SDFS_MAX_DIMS];   // grid[0] and grid[1]-grid[0] (utils.py:6-14)
+    const double *nodes;                 // [D][Q] shocks (quadrature nodes or Monte-Carlo draws)
+    const double *weights;               // [Q]
+    double p[18];                        // model parameters, reference order
+    double beta, gamma, theta, mu_c, phi_c;
+    int64_t N;
+    int64_t row_begin, row_end;          // states owned by this rank
+};
+
 struct sdfs_factors {
     sdfs_ctx *ctx = nullptr;
     int model = 0;
@@ -120,6 +136,8 @@ struct sdfs_op {
     int storage = SDFS_STORAGE_DENSE;
     DenseView dv{};
     KronView kv{};
+    ContView cv{};
+    double *cont_mem = nullptr;        // grids + nodes + weights of a continuous-state operator
     sdfs_factors *factors = nullptr;   // borrowed (kept alive by the host wrapper)
     // owned device memory
     double *own_P = nullptr, *own_a_row = nullptr, *own_a_col = nullptr, *own_e_sdf = nullptr;
@@ -133,6 +151,9 @@ struct sdfs_op {
 };
 
 int op_ensure_work(sdfs_op *op, int n_vectors);
+static inline int64_t op_N(const sdfs_op *op) {
+    return op->storage == SDFS_STORAGE_DENSE ? op->dv.N : (op->storage == SDFS_STORAGE_KRON ? op->kv.N : op->cv.N);
+}
 
 // ---------------------------------------------------------------------------
 // Device helpers

@@ -19,6 +19,7 @@
 // (x0 = 0, atol2 = max(tol^2 <b,b>, atol^2), early-exit half step, breakdown codes).
 #include "common.cuh"
 #include "rowdot.cuh"
+#include "cont.cuh"
 
 bool comm_peers_ready(sdfs_ctx *ctx);
 void *comm_peer_arena(sdfs_ctx *ctx, int r);
@@ -226,10 +227,24 @@ struct DenseLoopOp {
     __device__ __forceinline__ const double *a_col() const { return dv.a_col; }
     __device__ __forceinline__ double beta() const { return dv.beta; }
     __device__ __forceinline__ double theta() const { return dv.theta; }
+    // hooks of the loop kernels: what is staged as the operator input, the column scaling of the
+    // linearised map, the row factor of d = beta s^((1-theta)/theta) rowfac
+    static constexpr bool kNeedsW = false;
+    __device__ __forceinline__ double stage_T(int64_t n, double w) const { return dv.a_col[n] * pow(w, dv.theta); }
+    __device__ __forceinline__ double stage_c(int64_t n, double w) const { return dv.a_col[n] * pow(w, dv.theta - 1.0); }
+    __device__ __forceinline__ double rowfac(int64_t n) const { return dv.a_row[n]; }
+    // linear map on the staged vector: epi(n, (P xin)[n])
     template <class Epi>
     __device__ __forceinline__ bool apply(cg::grid_group &, const LoopEnv &, unsigned long long &, Scratch &sc,
-                                          const double *xin, Epi &&epi) const {
+                                          const double *xin, const double *, Epi &&epi) const {
         dense_pass<1>(dv, xin, xin, sc.rp, sc.st, [&](int64_t n, double s0, double) { epi(n, s0); });
+        return true;
+    }
+    // T pass: epi(n, s) with T w = 1 + beta s^(1/theta)
+    template <class Epi>
+    __device__ __forceinline__ bool apply_T(cg::grid_group &, const LoopEnv &, unsigned long long &, Scratch &sc,
+                                            const double *xin, Epi &&epi) const {
+        dense_pass<1>(dv, xin, xin, sc.rp, sc.st, [&](int64_t n, double s0, double) { epi(n, dv.a_row[n] * s0); });
         return true;
     }
 };
@@ -247,9 +262,18 @@ struct KronLoopOp {
     __device__ __forceinline__ const double *a_col() const { return kv.a_col; }
     __device__ __forceinline__ double beta() const { return kv.beta; }
     __device__ __forceinline__ double theta() const { return kv.theta; }
+    static constexpr bool kNeedsW = false;
+    __device__ __forceinline__ double stage_T(int64_t n, double w) const { return kv.a_col[n] * pow(w, kv.theta); }
+    __device__ __forceinline__ double stage_c(int64_t n, double w) const { return kv.a_col[n] * pow(w, kv.theta - 1.0); }
+    __device__ __forceinline__ double rowfac(int64_t n) const { return kv.a_row[n]; }
+    template <class Epi>
+    __device__ __forceinline__ bool apply_T(cg::grid_group &grid, const LoopEnv &env, unsigned long long &epoch,
+                                            Scratch &sc, const double *xin, Epi &&epi) const {
+        return apply(grid, env, epoch, sc, xin, nullptr, [&](int64_t n, double s) { epi(n, kv.a_row[n] * s); });
+    }
     template <class Epi>
     __device__ __forceinline__ bool apply(cg::grid_group &grid, const LoopEnv &env, unsigned long long &epoch,
-                                          Scratch &sc, const double *xin, Epi &&epi) const {
+                                          Scratch &sc, const double *xin, const double *, Epi &&epi) const {
         const double *in = xin;
         for (int m = 0; m < kv.n_modes - 1; ++m) {
             double *out = (m & 1) ? tmp1 : tmp0;
@@ -258,6 +282,36 @@ struct KronLoopOp {
             in = out;
         }
         kron_mode_apply(kv, kv.n_modes - 1, in, sc.smat, [&](int64_t idx, double s) { epi(idx, s); });
+        return true;
+    }
+};
+
+// Continuous-state operator (cont.cuh): the staged vector is w itself, the linearised map needs
+// the full current w beside the vector it is applied to.
+struct ContLoopOp {
+    static constexpr int kMinBlocks = 2;
+    static constexpr bool kNeedsW = true;
+    ContView cv;
+    __host__ __device__ size_t dyn_smem() const { return 0; }
+    __device__ __forceinline__ void init(Scratch &) const {}
+    __device__ __forceinline__ int64_t N() const { return cv.N; }
+    __device__ __forceinline__ int64_t row_begin() const { return cv.row_begin; }
+    __device__ __forceinline__ int64_t row_end() const { return cv.row_end; }
+    __device__ __forceinline__ double beta() const { return cv.beta; }
+    __device__ __forceinline__ double theta() const { return cv.theta; }
+    __device__ __forceinline__ double stage_T(int64_t, double w) const { return w; }
+    __device__ __forceinline__ double stage_c(int64_t, double) const { return 1.0; }
+    __device__ __forceinline__ double rowfac(int64_t n) const { return cont_rowfac(cv, n); }
+    template <class Epi>
+    __device__ __forceinline__ bool apply_T(cg::grid_group &, const LoopEnv &, unsigned long long &, Scratch &,
+                                            const double *xin, Epi &&epi) const {
+        cont_pass<0>(cv, xin, nullptr, [&](int64_t n, double kg, double) { epi(n, kg); });
+        return true;
+    }
+    template <class Epi>
+    __device__ __forceinline__ bool apply(cg::grid_group &, const LoopEnv &, unsigned long long &, Scratch &,
+                                          const double *xin, const double *wfull, Epi &&epi) const {
+        cont_pass<1>(cv, wfull, xin, [&](int64_t n, double, double l) { epi(n, l); });
         return true;
     }
 };
@@ -288,14 +342,13 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_sa_loop(const 
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
     const int64_t rb = op.row_begin(), re = op.row_end();
-    const double theta = op.theta(), beta = op.beta(), inv_theta = 1.0 / op.theta();
-    const double *a_row = op.a_row(), *a_col = op.a_col();
+    const double beta = op.beta(), inv_theta = 1.0 / op.theta();
 
-    // x = a_col * w0^theta for own rows, broadcast to every rank; w[0] = w0
+    // stage the operator input of w0 for own rows, broadcast to every rank; w[0] = w0
     for (int64_t n = rb + tid; n < re; n += nth) {
         const double w0 = a.w_init[n];
         a.w[0][n] = w0;
-        store_all_ranks(env, 0, n, a_col[n] * pow(w0, theta));
+        store_all_ranks(env, 0, n, op.stage_T(n, w0));
     }
     if (!all_sync(grid, env, epoch)) return;
 
@@ -306,10 +359,10 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_sa_loop(const 
         const double *w_cur = a.w[cur];
         double *w_nxt = a.w[nxt];
         double part[1] = {0.0};
-        bool ok = op.apply(grid, env, epoch, sc, env.xin[env.rank][cur], [&](int64_t n, double s) {
-            const double y = 1.0 + beta * pow(a_row[n] * s, inv_theta);
+        bool ok = op.apply_T(grid, env, epoch, sc, env.xin[env.rank][cur], [&](int64_t n, double s) {
+            const double y = 1.0 + beta * pow(s, inv_theta);
             w_nxt[n] = y;
-            store_all_ranks(env, nxt, n, a_col[n] * pow(y, theta));
+            store_all_ranks(env, nxt, n, op.stage_T(n, y));
             part[0] = nanmax(part[0], fabs(y - w_cur[n]));
         });
         if (!ok) return;
@@ -375,7 +428,7 @@ __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &
         if (!all_sync(grid, env, epoch)) return false;
         // D: q = J p = d .* P(c .* p) - p ; <rhat,q>
         double v1[1] = {0.0};
-        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double sum) {
+        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], env.xin[env.rank][1], [&](int64_t n, double sum) {
                 const double qn = a.d[n] * sum - a.p[n];
                 a.q[n] = qn;
                 v1[0] += a.rhat[n] * qn;
@@ -394,7 +447,7 @@ __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &
         const bool exit_early = v2[0] < atol2;
         // F: t = J s ; <t,s>, <t,t>
         double v3[2] = {0.0, 0.0};
-        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double sum) {
+        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], env.xin[env.rank][1], [&](int64_t n, double sum) {
                 const double sn = a.s[n];
                 const double tn = a.d[n] * sum - sn;
                 a.t[n] = tn;
@@ -473,7 +526,7 @@ __device__ __forceinline__ bool gmres_device(cg::grid_group &grid, const Op &op,
             double *Vj = a.V + (long long)j * a.ldv;
             double *Wv = a.V + (long long)(j + 1) * a.ldv;
             // w = J V_j
-            if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double sum) {
+            if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], env.xin[env.rank][1], [&](int64_t n, double sum) {
                     Wv[n] = a.d[n] * sum - Vj[n];
                 })) return false;
             its += 1;
@@ -568,7 +621,7 @@ __device__ __forceinline__ bool gmres_device(cg::grid_group &grid, const Op &op,
         if (!all_sync(grid, env, epoch)) return false;
         // true residual r = b - J x
         double rv[1] = {0.0};
-        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double sum) {
+        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], env.xin[env.rank][1], [&](int64_t n, double sum) {
                 const double rn = a.g[n] - (a.d[n] * sum - a.x[n]);
                 a.r[n] = rn;
                 rv[0] += rn * rn;
@@ -597,14 +650,14 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_newton_loop(co
     const int64_t rb = op.row_begin(), re = op.row_end();
     const double theta = op.theta(), beta = op.beta();
     const double inv_theta = 1.0 / theta, d_exp = (1.0 - theta) / theta;
-    const double *a_row = op.a_row(), *a_col = op.a_col();
 
-    // A: w = w0 ; xin = a_col w^theta ; c = a_col w^(theta-1)
+    // A: w = w0 ; staged operator input ; column scaling c of the linearised map
     for (int64_t n = rb + tid; n < re; n += nth) {
         const double w0 = a.w_init[n];
         a.w[n] = w0;
-        a.c[n] = a_col[n] * pow(w0, theta - 1.0);
-        store_all_ranks(env, 0, n, a_col[n] * pow(w0, theta));
+        a.c[n] = op.stage_c(n, w0);
+        store_all_ranks(env, 0, n, op.stage_T(n, w0));
+        if (Op::kNeedsW) store_all_ranks(env, 1, n, w0);
     }
     if (!all_sync(grid, env, epoch)) return;
 
@@ -613,12 +666,10 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_newton_loop(co
     while (error > a.tol && it < a.max_iter) {
         // B: s = a_row P xin ; Tw ; g = Tw - w ; d ; Krylov init ; <g,g>
         double vb[1] = {0.0};
-        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double sum) {
-                const double ar = a_row[n];
-                const double sv = ar * sum;
+        if (!op.apply_T(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double sv) {
                 const double gn = (1.0 + beta * pow(sv, inv_theta)) - a.w[n];
                 a.g[n] = gn;
-                a.d[n] = beta * pow(sv, d_exp) * ar;
+                a.d[n] = beta * pow(sv, d_exp) * op.rowfac(n);
                 a.r[n] = gn; a.rhat[n] = gn; a.p[n] = gn; a.q[n] = gn;
                 a.x[n] = 0.0;
                 vb[0] += gn * gn;
@@ -639,8 +690,9 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_newton_loop(co
             const double wn = a.w[n] - xn;
             a.w[n] = wn;
             vh[0] = nanmax(vh[0], fabs(xn));
-            a.c[n] = a_col[n] * pow(wn, theta - 1.0);
-            store_all_ranks(env, 0, n, a_col[n] * pow(wn, theta));
+            a.c[n] = op.stage_c(n, wn);
+            store_all_ranks(env, 0, n, op.stage_T(n, wn));
+            if (Op::kNeedsW) store_all_ranks(env, 1, n, wn);
         }
         if (!grid_allreduce<1, true>(grid, env, epoch, SET_H, vh, smem)) return;
         error = vh[0];
@@ -725,8 +777,7 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_anderson_loop(
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
     const int64_t rb = op.row_begin(), re = op.row_end();
-    const double theta = op.theta(), beta = op.beta(), inv_theta = 1.0 / op.theta();
-    const double *a_row = op.a_row(), *a_col = op.a_col();
+    const double beta = op.beta(), inv_theta = 1.0 / op.theta();
     const int m = a.m;
     for (int e = threadIdx.x; e < AND_MAX_HIST * AND_MAX_HIST; e += blockDim.x) sG[e] = 0.0;
     // x = x0 ; history tiled with x0 (jaxopt init_state), residual history zero ; xin = a_col x^theta
@@ -734,7 +785,7 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_anderson_loop(
         const double w0 = a.w_init[n];
         a.x[n] = w0;
         for (int i = 0; i < m; ++i) { a.X[i * a.ldv + n] = w0; a.R[i * a.ldv + n] = 0.0; }
-        store_all_ranks(env, 0, n, a_col[n] * pow(w0, theta));
+        store_all_ranks(env, 0, n, op.stage_T(n, w0));
     }
     if (!all_sync(grid, env, epoch)) return;
     long long k = 0;
@@ -742,8 +793,8 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_anderson_loop(
     while (error > a.tol && k < a.max_iter) {
         const int pos = (int)(k % m);
         // f(x), residual, history update
-        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double s) {
-                const double y = 1.0 + beta * pow(a_row[n] * s, inv_theta);
+        if (!op.apply_T(grid, env, epoch, sc, env.xin[env.rank][0], [&](int64_t n, double s) {
+                const double y = 1.0 + beta * pow(s, inv_theta);
                 const double xn = a.x[n];
                 a.fx[n] = y;
                 a.X[pos * a.ldv + n] = xn;
@@ -787,7 +838,7 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_anderson_loop(
                 xn = a.fx[n];
             }
             a.x[n] = xn;
-            store_all_ranks(env, 0, n, a_col[n] * pow(xn, theta));
+            store_all_ranks(env, 0, n, op.stage_T(n, xn));
         }
         if (!all_sync(grid, env, epoch)) return;
         ++k;
@@ -809,7 +860,7 @@ static int build_env(sdfs_op *op, LoopEnv *env) {
     env->rank = ctx->rank;
     env->nranks = ctx->nranks;
     env->status = (LoopStatus *)ctx->d_status;
-    const int64_t N = (op->storage == SDFS_STORAGE_DENSE) ? op->dv.N : op->kv.N;
+    const int64_t N = op_N(op);
     const bool sharded = ctx->nranks > 1 && op->storage == SDFS_STORAGE_DENSE &&
                          (op->dv.row_end - op->dv.row_begin) < op->dv.N;
     if (!sharded) {   // single GPU, factor form, or a replicated dense operator: purely local loop
@@ -911,6 +962,11 @@ int sdfs_solve_sa(sdfs_op *op, const double *d_w_init, double tol, int64_t max_i
         TRY(coop_grid(ctx, k_sa_loop<DenseLoopOp>, lop.dyn_smem(), 1, dense_groups(op->dv), env.nranks > 1, &grid));
         void *args[] = {&lop, &a, &env};
         CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sa_loop<DenseLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, lop.dyn_smem(), ctx->stream));
+    } else if (op->storage == SDFS_STORAGE_CONT) {
+        ContLoopOp lop{op->cv};
+        TRY(coop_grid(ctx, k_sa_loop<ContLoopOp>, 0, 2, (op->cv.N + 8) / 9, false, &grid));
+        void *args[] = {&lop, &a, &env};
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sa_loop<ContLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, 0, ctx->stream));
     } else {
         if (!op->kron_tmp[0]) {
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[0], (size_t)op->kv.N * sizeof(double)));
@@ -926,7 +982,7 @@ int sdfs_solve_sa(sdfs_op *op, const double *d_w_init, double tol, int64_t max_i
     TRY(finish_loop(ctx, hs, 0));
     if (env.nranks > 1) {
         *comm_epoch(ctx) = hs->epoch_end;   // every rank passed the same barriers
-        TRY(comm_allgather_rows(ctx, d_w_out, op->dv.N));
+        TRY(comm_allgather_rows(ctx, d_w_out, op_N(op)));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (iters) *iters = hs->iters;
@@ -944,7 +1000,7 @@ int sdfs_solve_anderson(sdfs_op *op, const double *d_w_init, double tol, int64_t
     if (!ctx->coop_supported) return sdfs_set_error(ctx, SDFS_ERR_UNSUPPORTED, "device lacks cooperative launch");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const bool dense = op->storage == SDFS_STORAGE_DENSE;
-    const int64_t N = dense ? op->dv.N : op->kv.N;
+    const int64_t N = op_N(op);
     TRY(op_ensure_work(op, 16 + 2 * AND_MAX_HIST));
     LoopEnv env;
     TRY(build_env(op, &env));
@@ -962,6 +1018,11 @@ int sdfs_solve_anderson(sdfs_op *op, const double *d_w_init, double tol, int64_t
         TRY(coop_grid(ctx, k_anderson_loop<DenseLoopOp>, lop.dyn_smem(), 1, dense_groups(op->dv), env.nranks > 1, &grid));
         void *args[] = {&lop, &a, &env};
         CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_anderson_loop<DenseLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, lop.dyn_smem(), ctx->stream));
+    } else if (op->storage == SDFS_STORAGE_CONT) {
+        ContLoopOp lop{op->cv};
+        TRY(coop_grid(ctx, k_anderson_loop<ContLoopOp>, 0, 2, (N + 8) / 9, false, &grid));
+        void *args[] = {&lop, &a, &env};
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_anderson_loop<ContLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, 0, ctx->stream));
     } else {
         if (!op->kron_tmp[0]) {
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[0], (size_t)N * sizeof(double)));
@@ -997,7 +1058,7 @@ int sdfs_solve_newton(sdfs_op *op, const double *d_w_init, double tol, int64_t m
     if (!ctx->coop_supported) return sdfs_set_error(ctx, SDFS_ERR_UNSUPPORTED, "device lacks cooperative launch");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const bool dense = op->storage == SDFS_STORAGE_DENSE;
-    const int64_t N = dense ? op->dv.N : op->kv.N;
+    const int64_t N = op_N(op);
     const int nvec = 16 + (krylov == SDFS_KRYLOV_GMRES ? restart + 1 : 0);
     TRY(op_ensure_work(op, nvec));
     LoopEnv env;
@@ -1021,6 +1082,11 @@ int sdfs_solve_newton(sdfs_op *op, const double *d_w_init, double tol, int64_t m
         TRY(coop_grid(ctx, k_newton_loop<DenseLoopOp>, lop.dyn_smem(), 1, dense_groups(op->dv), env.nranks > 1, &grid));
         void *args[] = {&lop, &a, &env};
         CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_newton_loop<DenseLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, lop.dyn_smem(), ctx->stream));
+    } else if (op->storage == SDFS_STORAGE_CONT) {
+        ContLoopOp lop{op->cv};
+        TRY(coop_grid(ctx, k_newton_loop<ContLoopOp>, 0, 2, (N + 8) / 9, false, &grid));
+        void *args[] = {&lop, &a, &env};
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_newton_loop<ContLoopOp>, dim3(grid), dim3(SDFS_THREADS), args, 0, ctx->stream));
     } else {
         if (!op->kron_tmp[0]) {
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[0], (size_t)N * sizeof(double)));

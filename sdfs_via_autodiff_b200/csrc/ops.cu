@@ -1,6 +1,7 @@
 // Operator handles and single applications: T, JVP, SDF, plain P x.
 #include "common.cuh"
 #include "rowdot.cuh"
+#include "cont.cuh"
 
 int factors_to_kron(const sdfs_factors *f, KronView *kv);
 int launch_build_scalings(sdfs_ctx *ctx, const sdfs_factors *f, const KronView &kv, double gamma,
@@ -122,7 +123,7 @@ int op_ensure_work(sdfs_op *op, int n_vectors) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (op->work) CUDA_TRY(ctx, cudaFree(op->work));
     op->work = nullptr;
-    const int64_t N = (op->storage == SDFS_STORAGE_DENSE) ? op->dv.N : op->kv.N;
+    const int64_t N = op_N(op);
     op->ldv = round_up(N, 64) + 64;
     CUDA_TRY(ctx, cudaMalloc(&op->work, (size_t)n_vectors * op->ldv * sizeof(double)));
     CUDA_TRY(ctx, cudaMemsetAsync(op->work, 0, (size_t)n_vectors * op->ldv * sizeof(double), ctx->stream));
@@ -156,6 +157,34 @@ static int launch_dense_apply(sdfs_ctx *ctx, const DenseView &dv, const double *
         CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
         ctx->prof_used += 2;
     }
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SDFS_OK;
+}
+
+// Continuous-state operator: T w, and the fused T + J_T(w) v sweep (one loop over the shock nodes)
+__global__ void __launch_bounds__(256) k_cont_T(ContView cv, const double *__restrict__ w, double *__restrict__ out) {
+    const double inv_theta = 1.0 / cv.theta;
+    cont_pass<0>(cv, w, nullptr, [&](int64_t n, double kg, double) { out[n] = 1.0 + cv.beta * pow(kg, inv_theta); });
+}
+__global__ void __launch_bounds__(256) k_cont_jvp(ContView cv, const double *__restrict__ w, const double *__restrict__ v,
+                                                  double *__restrict__ out) {
+    // J_T(w) v = beta s^((1-theta)/theta) const(x) L(v),  s = Kg(w)   (derivative of 1 + beta s^(1/theta))
+    const double d_exp = (1.0 - cv.theta) / cv.theta;
+    cont_pass<2>(cv, w, v, [&](int64_t n, double kg, double l) {
+        out[n] = cv.beta * pow(kg, d_exp) * cont_rowfac(cv, n) * l;
+    });
+}
+
+static int run_cont(sdfs_op *op, int which, const double *d_w, const double *d_v, double *d_out) {
+    sdfs_ctx *ctx = op->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const ContView &cv = op->cv;
+    int64_t g = (cv.N * 32 + 255) / 256;                 // one warp per state
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    const int grid = (int)(g < cap ? (g > 0 ? g : 1) : cap);
+    if (which == 0) k_cont_T<<<grid, 256, 0, ctx->stream>>>(cv, d_w, d_out);
+    else k_cont_jvp<<<grid, 256, 0, ctx->stream>>>(cv, d_w, d_v, d_out);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return SDFS_OK;
@@ -307,11 +336,66 @@ int sdfs_op_from_factors(sdfs_ctx *ctx, sdfs_factors *f, int storage, sdfs_op **
     return SDFS_OK;
 }
 
+// Continuous-state operator: h_grids = the D uniform grids concatenated (sizes h_sizes), h_nodes =
+// D x Q shocks (row d = shocks of state component d), h_weights = Q weights.
+int sdfs_op_continuous(sdfs_ctx *ctx, int model, const double *h_params, const int32_t *h_sizes,
+                       const double *h_grids, const double *h_nodes, const double *h_weights, int64_t Q,
+                       sdfs_op **out) {
+    ARG_CHECK(ctx, ctx && h_params && h_sizes && h_grids && h_nodes && h_weights && out && Q >= 1 && Q < (1ll << 30));
+    ARG_CHECK(ctx, model == SDFS_MODEL_SSY || model == SDFS_MODEL_GCY);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int D = (model == SDFS_MODEL_SSY) ? 4 : 6;
+    int64_t N = 1, gtot = 0;
+    for (int d = 0; d < D; ++d) {
+        if (h_sizes[d] < 2) return sdfs_set_error(ctx, SDFS_ERR_ARG, "grid %d needs at least 2 points", d);
+        N *= h_sizes[d];
+        gtot += h_sizes[d];
+    }
+    sdfs_op *op = new sdfs_op();
+    op->ctx = ctx;
+    op->storage = SDFS_STORAGE_CONT;
+    const size_t doubles = (size_t)gtot + (size_t)D * Q + (size_t)Q;
+    cudaError_t e = cudaMalloc(&op->cont_mem, doubles * sizeof(double));
+    if (e != cudaSuccess) { delete op; return sdfs_set_error(ctx, SDFS_ERR_NOMEM, "continuous operator tables: %s", cudaGetErrorString(e)); }
+    ContView &cv = op->cv;
+    memset(&cv, 0, sizeof(cv));
+    cv.model = model; cv.D = D; cv.Q = (int)Q; cv.N = N;
+    double *dptr = op->cont_mem;
+    const double *hg = h_grids;
+    for (int d = 0; d < D; ++d) {
+        cv.n[d] = h_sizes[d];
+        cv.grid[d] = dptr;
+        cv.g0[d] = hg[0];
+        cv.intv[d] = hg[1] - hg[0];
+        cudaMemcpyAsync(dptr, hg, h_sizes[d] * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        dptr += h_sizes[d];
+        hg += h_sizes[d];
+    }
+    cv.nodes = dptr;
+    cudaMemcpyAsync(dptr, h_nodes, (size_t)D * Q * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    dptr += (size_t)D * Q;
+    cv.weights = dptr;
+    cudaMemcpyAsync(dptr, h_weights, (size_t)Q * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    const int np = (model == SDFS_MODEL_SSY) ? 13 : 18;
+    for (int i = 0; i < np; ++i) cv.p[i] = h_params[i];
+    double psi;
+    if (model == SDFS_MODEL_SSY) { cv.beta = h_params[0]; cv.gamma = h_params[1]; psi = h_params[2]; cv.mu_c = h_params[3]; cv.phi_c = h_params[6]; }
+    else { cv.beta = h_params[0]; psi = h_params[1]; cv.gamma = h_params[2]; cv.mu_c = h_params[5]; cv.phi_c = h_params[6]; }
+    cv.theta = (1.0 - cv.gamma) / (1.0 - 1.0 / psi);
+    cv.row_begin = 0;
+    cv.row_end = N;      // states are not sharded: every rank evaluates the whole grid
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { sdfs_op_destroy(op); return sdfs_set_error(ctx, SDFS_ERR_CUDA, "continuous operator upload: %s", cudaGetErrorString(e)); }
+    *out = op;
+    return SDFS_OK;
+}
+
 int sdfs_op_destroy(sdfs_op *op) {
     if (!op) return SDFS_OK;
     sdfs_ctx *ctx = op->ctx;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (op->cont_mem) cudaFree(op->cont_mem);
     if (op->own_P) cudaFree(op->own_P);
     if (op->own_a_row) cudaFree(op->own_a_row);
     if (op->own_a_col) cudaFree(op->own_a_col);
@@ -328,12 +412,13 @@ int sdfs_op_info(sdfs_op *op, int64_t *N, int64_t *ld, int64_t *row_begin, int64
                  double *theta, int *storage) {
     if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_info: NULL op");
     const bool dense = op->storage == SDFS_STORAGE_DENSE;
-    if (N) *N = dense ? op->dv.N : op->kv.N;
+    const bool cont = op->storage == SDFS_STORAGE_CONT;
+    if (N) *N = op_N(op);
     if (ld) *ld = dense ? op->dv.ld : 0;
     if (row_begin) *row_begin = dense ? op->dv.row_begin : 0;
-    if (row_end) *row_end = dense ? op->dv.row_end : op->kv.N;
-    if (beta) *beta = dense ? op->dv.beta : op->kv.beta;
-    if (theta) *theta = dense ? op->dv.theta : op->kv.theta;
+    if (row_end) *row_end = dense ? op->dv.row_end : op_N(op);
+    if (beta) *beta = dense ? op->dv.beta : (cont ? op->cv.beta : op->kv.beta);
+    if (theta) *theta = dense ? op->dv.theta : (cont ? op->cv.theta : op->kv.theta);
     if (storage) *storage = op->storage;
     return SDFS_OK;
 }
@@ -374,6 +459,7 @@ int sdfs_op_set_preferences(sdfs_op *op, double gamma, double psi, double beta) 
 int sdfs_op_apply_T(sdfs_op *op, const double *d_w_in, double *d_w_out) {
     if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_apply_T: NULL op");
     ARG_CHECK(op->ctx, d_w_in && d_w_out);
+    if (op->storage == SDFS_STORAGE_CONT) return run_cont(op, 0, d_w_in, nullptr, d_w_out);
     const bool dense = op->storage == SDFS_STORAGE_DENSE;
     EpiArgs e{0, dense ? op->dv.a_row : op->kv.a_row, nullptr, nullptr, dense ? op->dv.beta : op->kv.beta,
               dense ? op->dv.theta : op->kv.theta, d_w_out, nullptr};
@@ -383,6 +469,7 @@ int sdfs_op_apply_T(sdfs_op *op, const double *d_w_in, double *d_w_out) {
 int sdfs_op_apply_jvp(sdfs_op *op, const double *d_w, const double *d_v, double *d_out) {
     if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_apply_jvp: NULL op");
     ARG_CHECK(op->ctx, d_w && d_v && d_out);
+    if (op->storage == SDFS_STORAGE_CONT) return run_cont(op, 1, d_w, d_v, d_out);
     const bool dense = op->storage == SDFS_STORAGE_DENSE;
     EpiArgs e{1, dense ? op->dv.a_row : op->kv.a_row, nullptr, nullptr, dense ? op->dv.beta : op->kv.beta,
               dense ? op->dv.theta : op->kv.theta, d_out, nullptr};
@@ -392,6 +479,8 @@ int sdfs_op_apply_jvp(sdfs_op *op, const double *d_w, const double *d_v, double 
 int sdfs_op_apply_P(sdfs_op *op, const double *d_x, double *d_y) {
     if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_apply_P: NULL op");
     ARG_CHECK(op->ctx, d_x && d_y);
+    if (op->storage == SDFS_STORAGE_CONT)
+        return sdfs_set_error(op->ctx, SDFS_ERR_UNSUPPORTED, "continuous-state operators have no transition matrix P");
     EpiArgs e{3, nullptr, nullptr, nullptr, 0.0, 1.0, d_y, nullptr};
     return run_apply(op, 3, nullptr, d_x, e, true, false);
 }
@@ -420,6 +509,8 @@ int sdfs_op_bench_pass(sdfs_op *op, int mode, int reps, double *avg_ms) {
 
 int sdfs_op_sdf(sdfs_op *op, const double *d_w, double *d_qf, double *d_euler) {
     if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_op_sdf: NULL op");
+    if (op->storage == SDFS_STORAGE_CONT)
+        return sdfs_set_error(op->ctx, SDFS_ERR_UNSUPPORTED, "SDF evaluation is defined for the discretised Markov-grid operators");
     const bool dense = op->storage == SDFS_STORAGE_DENSE;
     const double *es = dense ? op->dv.e_sdf : op->kv.e_sdf;
     ARG_CHECK(op->ctx, d_w && (d_qf || d_euler));

@@ -461,6 +461,63 @@ def test_loglinear_guess_on_device_and_warm_start():
     np.testing.assert_allclose(np.asarray(w_warm), np.asarray(w_cold), rtol=RTOL_W)
 
 
+def test_continuous_state_operators():
+    """'Next' row: continuous-state T (quadrature / Monte-Carlo + multilinear interpolation) against
+    the package oracle's independent restatement (parity with the JAX original is unpinned)."""
+    from oracle.continuous import ContSSY, ContGCY, qnwnorm, build_grid_ssy, build_grid_gcy
+    # grids and quadrature rule
+    sizes = (4, 5, 6, 7)
+    for a, b in zip(S.build_grid(S.SSY(), *sizes), build_grid_ssy(O.SSY(), sizes)):
+        np.testing.assert_allclose(a, b, rtol=1e-15)
+    gs = (3, 3, 3, 3, 4, 4)
+    for a, b in zip(S.build_grid(S.GCY(), *gs), build_grid_gcy(O.GCY(), gs)):
+        np.testing.assert_allclose(a, b, rtol=1e-15)
+    nodes, weights = S.gauss_hermite_normal(3, 4)
+    n_ref, w_ref = qnwnorm([3] * 4)
+    np.testing.assert_allclose(nodes, n_ref.T, rtol=1e-15)
+    np.testing.assert_allclose(weights, w_ref, rtol=1e-14)
+    rng = np.random.default_rng(5)
+    # SSY, quadrature d = 3
+    ref = ContSSY(O.SSY(), sizes, nodes, weights)
+    grids, T = S.make_T_continuous(S.SSY(), sizes, d=3)
+    w = 700 + 200 * rng.random(sizes)
+    v = rng.standard_normal(sizes)
+    np.testing.assert_allclose(np.asarray(T(w)), ref.T(w), rtol=1e-12)
+    np.testing.assert_allclose(np.asarray(T.jvp(w, v)), ref.jvp(w, v), rtol=1e-10, atol=1e-12)
+    # iterates of successive approximation agree step by step
+    ws, k = S.successive_approx(T, np.full(sizes, 800.0), tol=0.0, max_iter=40, verbose=False)
+    wr = np.full(sizes, 800.0)
+    for _ in range(40):
+        wr = ref.T(wr)
+    np.testing.assert_allclose(np.asarray(ws), wr, rtol=1e-12)
+    # Newton (tight inner solve) reaches the oracle's fixed point; Anderson agrees with it
+    wn, kn = S.newton_solver(T, np.full(sizes, 800.0), tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12, verbose=False)
+    w_fix, _ = O.newton_solver(ref.T, np.full(sizes, 800.0), jvp=ref.jvp, tol=1e-9, bicgstab_atol=1e-11, verbose=False)
+    w_fix, _ = O.successive_approx(ref.T, w_fix, tol=1e-10, max_iter=200, verbose=False)
+    np.testing.assert_allclose(np.asarray(wn), w_fix, rtol=1e-9)
+    wa, ka = S.anderson_solver(T, np.full(sizes, 800.0), verbose=False)
+    np.testing.assert_allclose(np.asarray(wa), w_fix, rtol=1e-6)
+    # Monte-Carlo rule with given draws (weights 1/Q)
+    draws = rng.standard_normal((4, 100))
+    ref_mc = ContSSY(O.SSY(), sizes, draws, np.full(100, 0.01))
+    _, Tmc = S.make_T_continuous(S.SSY(), sizes, method="monte_carlo", mc_draws=draws)
+    np.testing.assert_allclose(np.asarray(Tmc(w)), ref_mc.T(w), rtol=1e-12)
+    # GCY, quadrature d = 2 (64 nodes, 64 interpolation corners)
+    n6, w6 = S.gauss_hermite_normal(2, 6)
+    gref = ContGCY(O.GCY(), gs, n6, w6)
+    _, Tg = S.make_T_continuous(S.GCY(), gs, d=2)
+    wg = 350 + 100 * rng.random(gs)
+    vg = rng.standard_normal(gs)
+    np.testing.assert_allclose(np.asarray(Tg(wg)), gref.T(wg), rtol=1e-12)
+    np.testing.assert_allclose(np.asarray(Tg.jvp(wg, vg)), gref.jvp(wg, vg), rtol=1e-10, atol=1e-12)
+    # the reference's driver surface
+    g2, w2 = S.wc_ratio_continuous(S.SSY(), 4, 5, 6, 7, d=3, algorithm="newton", tol=1e-7, verbose=False)
+    assert len(g2) == 4 and np.asarray(w2).shape == sizes
+    np.testing.assert_allclose(np.asarray(w2), w_fix, rtol=1e-5)
+    with pytest.raises(S.SdfsError):
+        T.sdf(w)
+
+
 def test_error_behaviour_and_pinned_buffers():
     ctx = S.Context.default()
     # dense P that cannot fit: a clear out-of-memory error, not a crash (8.8 TB at 10^6 states)
