@@ -17,7 +17,7 @@ from numpy.polynomial.hermite import hermgauss
 from ._lib import lib, check
 from .device import Context
 from .operator import WCOperator, MODEL_SSY, MODEL_GCY
-from . import solvers as _sv          # module (the package attribute `solvers` is the dict)
+from .solvers import solvers as _solver_table, successive_approx as _successive_approx
 
 
 def _is_gcy(model):
@@ -126,10 +126,10 @@ def wc_ratio_continuous(model, *grid_sizes, num_std_devs=3.2, d=5, mc_draw_size=
     if w_init is None:
         w_init = T.ctx.full(T.shapes, 1.0)
     try:
-        fn = _sv.solvers[algorithm]
+        fn = _solver_table[algorithm]
     except KeyError:
         print(f"Algorithm {algorithm} not found.  \nFalling back to successive approximation.\n")
-        fn = _sv.successive_approx
+        fn = _successive_approx
     w_star, _ = fn(T, w_init, tol=tol, verbose=verbose)
     if write_to_file:
         with open(filename, "wb") as f:
