@@ -133,6 +133,12 @@ int sdfs_op_from_factors(sdfs_ctx *ctx, sdfs_factors *f, int storage, sdfs_op **
 int sdfs_op_continuous(sdfs_ctx *ctx, int model, const double *h_params, const int32_t *h_sizes,
                        const double *h_grids, const double *h_nodes, const double *h_weights,
                        int64_t Q, sdfs_op **out);
+/* lin_interp (utils.py:17-23; construct_wstar_callable, ssy_wc_ratio_continuous.py:304-326):
+ * multilinear interpolation of d_vals (C-order tensor over D = 4 or 6 uniform grids, first value
+ * h_g0[d], spacing h_intv[d]) at M points; d_x is D x M row-major; nearest-edge extension. */
+int sdfs_interp_points(sdfs_ctx *ctx, int D, const int32_t *h_sizes, const double *h_g0,
+                       const double *h_intv, const double *d_vals, const double *d_x, int64_t M,
+                       double *d_out);
 int sdfs_op_destroy(sdfs_op *op);
 int sdfs_op_info(sdfs_op *op, int64_t *N, int64_t *ld, int64_t *row_begin,
                  int64_t *row_end, double *beta, double *theta, int *storage);

@@ -19,4 +19,4 @@ from .sdf import solve_ssy, solve_gcy, SDFResult                 # noqa: F401
 from .sweep import make_sweep_operator, sweep_apply_T, sweep_solve                      # noqa: F401
 from .loglinear import loglinear_guess                                               # noqa: F401
 from .continuous import (build_grid, T_fun_factory, make_T_continuous, wc_ratio_continuous,   # noqa: F401
-                         gauss_hermite_normal)
+                         gauss_hermite_normal, construct_wstar_callable, lin_interp, save_wstar)

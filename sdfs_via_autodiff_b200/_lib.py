@@ -65,6 +65,7 @@ _SIGS = {
     "sdfs_op_from_dense": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_f64, c_f64, P(c_vp)]),
     "sdfs_op_from_factors": (C.c_int, [c_vp, c_vp, C.c_int, P(c_vp)]),
     "sdfs_op_continuous": (C.c_int, [c_vp, C.c_int, P(c_f64), P(C.c_int32), P(c_f64), P(c_f64), P(c_f64), c_i64, P(c_vp)]),
+    "sdfs_interp_points": (C.c_int, [c_vp, C.c_int, P(C.c_int32), P(c_f64), P(c_f64), c_vp, c_vp, c_i64, c_vp]),
     "sdfs_op_destroy": (C.c_int, [c_vp]),
     "sdfs_op_info": (C.c_int, [c_vp, P(c_i64), P(c_i64), P(c_i64), P(c_i64), P(c_f64), P(c_f64), P(C.c_int)]),
     "sdfs_op_arrays": (C.c_int, [c_vp, P(c_vp), P(c_vp), P(c_vp), P(c_vp)]),

@@ -132,7 +132,47 @@ def wc_ratio_continuous(model, *grid_sizes, num_std_devs=3.2, d=5, mc_draw_size=
         fn = _successive_approx
     w_star, _ = fn(T, w_init, tol=tol, verbose=verbose)
     if write_to_file:
-        with open(filename, "wb") as f:
-            np.save(f, np.array(grids, dtype=object), allow_pickle=True)
-            np.save(f, np.asarray(w_star))
+        save_wstar(filename, grids, w_star)
     return grids, w_star
+
+
+def save_wstar(filename, grids, w_star):
+    """The reference's on-disk format (ssy_wc_ratio_continuous.py:291-295): two consecutive
+    np.save records in one file, the grids then w_star."""
+    same = len({len(g) for g in grids}) == 1
+    with open(filename, "wb") as f:
+        np.save(f, np.asarray(grids) if same else np.array([np.asarray(g) for g in grids], dtype=object),
+                allow_pickle=not same)
+        np.save(f, np.asarray(w_star))
+
+
+def lin_interp(x, fun_vals, grids, ctx=None):
+    """utils.py:17-23 on the device: x of shape (dim, M) -> M interpolated values."""
+    ctx = ctx or Context.default()
+    grids = [np.asarray(g, dtype=np.float64) for g in grids]
+    dim = len(grids)
+    xd = ctx.asarray(np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(dim, -1))) \
+        if not hasattr(x, "ptr") else x
+    vals = ctx.asarray(fun_vals)
+    M = xd.size // dim
+    out = ctx.empty((M,))
+    sizes = (C.c_int32 * dim)(*[g.size for g in grids])
+    g0 = (C.c_double * dim)(*[float(g[0]) for g in grids])
+    intv = (C.c_double * dim)(*[float(g[1] - g[0]) for g in grids])
+    check(lib.sdfs_interp_points(ctx.handle, dim, sizes, g0, intv, vals.ptr, xd.ptr, M, out.ptr), ctx.handle)
+    return out
+
+
+def construct_wstar_callable(w_star_vals=None, grids=None, datafile="w_star_data.npy"):
+    """Callable x -> w*(x) by linear interpolation over the grid (ssy_wc_ratio_continuous.py:304-326);
+    data are read from ``datafile`` when not given.  The values stay resident on the device."""
+    if w_star_vals is None or grids is None:
+        with open(datafile, "rb") as f:
+            grids = np.load(f, allow_pickle=True)
+            w_star_vals = np.load(f)
+    grids = [np.asarray(g, dtype=np.float64) for g in grids]
+    vals = Context.default().asarray(w_star_vals)
+
+    def w_star_func(x):
+        return lin_interp(x, vals, grids)
+    return w_star_func

@@ -176,6 +176,39 @@ __global__ void __launch_bounds__(256) k_cont_jvp(ContView cv, const double *__r
     });
 }
 
+// lin_interp (utils.py:17-23) at M arbitrary points: x is D x M row-major
+template <int D>
+__global__ void k_interp_points(ContView cv, const double *__restrict__ vals, const double *__restrict__ x, int64_t M,
+                                double *__restrict__ out) {
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+        double xn[D], o0, o1;
+#pragma unroll
+        for (int d = 0; d < D; ++d) xn[d] = x[(int64_t)d * M + m];
+        cont_interp<D, 1>(cv, xn, vals, vals, o0, o1);
+        out[m] = o0;
+    }
+}
+
+extern "C" int sdfs_interp_points(sdfs_ctx *ctx, int D, const int32_t *h_sizes, const double *h_g0, const double *h_intv,
+                                  const double *d_vals, const double *d_x, int64_t M, double *d_out) {
+    ARG_CHECK(ctx, ctx && h_sizes && h_g0 && h_intv && d_vals && d_x && d_out && M >= 0 && (D == 4 || D == 6));
+    if (M == 0) return SDFS_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ContView cv;
+    memset(&cv, 0, sizeof(cv));
+    cv.D = D;
+    for (int d = 0; d < D; ++d) {
+        ARG_CHECK(ctx, h_sizes[d] >= 2 && h_intv[d] != 0.0);
+        cv.n[d] = h_sizes[d]; cv.g0[d] = h_g0[d]; cv.intv[d] = h_intv[d];
+    }
+    const int grid = (int)((M + 255) / 256 < 4096 ? (M + 255) / 256 : 4096);
+    if (D == 4) k_interp_points<4><<<grid, 256, 0, ctx->stream>>>(cv, d_vals, d_x, M, d_out);
+    else k_interp_points<6><<<grid, 256, 0, ctx->stream>>>(cv, d_vals, d_x, M, d_out);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SDFS_OK;
+}
+
 static int run_cont(sdfs_op *op, int which, const double *d_w, const double *d_v, double *d_out) {
     sdfs_ctx *ctx = op->ctx;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));

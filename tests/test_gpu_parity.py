@@ -516,6 +516,17 @@ def test_continuous_state_operators():
     np.testing.assert_allclose(np.asarray(w2), w_fix, rtol=1e-5)
     with pytest.raises(S.SdfsError):
         T.sdf(w)
+    # persistence + interpolated w* callable (ssy_wc_ratio_continuous.py:291-326)
+    import tempfile
+    from oracle.continuous import lin_interp as ref_interp
+    pts = np.stack([rng.uniform(g[0] - 0.3 * (g[-1] - g[0]), g[-1] + 0.3 * (g[-1] - g[0]), 500) for g in g2])
+    with tempfile.TemporaryDirectory() as tmp:
+        fn = os.path.join(tmp, "w_star_data.npy")
+        S.save_wstar(fn, g2, w2)
+        f_disk = S.construct_wstar_callable(datafile=fn)
+        np.testing.assert_allclose(np.asarray(f_disk(pts)), ref_interp(pts, np.asarray(w2), g2), rtol=1e-13)
+    f_mem = S.construct_wstar_callable(w2, g2)
+    np.testing.assert_allclose(np.asarray(f_mem(pts)), ref_interp(pts, np.asarray(w2), g2), rtol=1e-13)
 
 
 def test_error_behaviour_and_pinned_buffers():
