@@ -1,30 +1,32 @@
-"""SSY (Schorfheide-Song-Yaron) parameter object -- host mirror of
-/root/reference/code/ssy/ssy_model.py:50-81: same keyword names, defaults,
-``.θ`` and ``.params`` order (β, γ, ψ, μ_c, ρ, ϕ_z, ϕ_c, ρ_z, ρ_c, ρ_λ, s_z, s_c, s_λ).
-
-State x = (h_λ, h_c, h_z, z), indexed (l, k, i, j).
+"""SSY (Schorfheide-Song-Yaron) parameter object: host mirror of the reference's ``SSY``
+(/root/reference/code/ssy/ssy_model.py:50-81) -- same keyword names, defaults (Table VII of the
+paper), ``.θ`` and ``.params`` order.  State x = (h_λ, h_c, h_z, z), indexed (l, k, i, j).
 """
-import numpy as np
+import math
+
+from ._params import ParameterSet
+
+_SIGMA_BAR = 0.0035
 
 
-class SSY:
-    def __init__(self,
-                 β=0.999, γ=8.89, ψ=1.97,
-                 ρ=0.987, ρ_z=0.992, ρ_c=0.991, ρ_λ=0.959,
-                 s_z=np.sqrt(0.0039), s_c=np.sqrt(0.0096), s_λ=0.0004,
-                 μ_c=0.0016,
-                 ϕ_z=0.215 * 0.0035 * np.sqrt(1 - 0.987 ** 2),
-                 ϕ_c=1.00 * 0.0035):
-        self.β, self.γ, self.ψ = β, γ, ψ
-        self.μ_c, self.ϕ_z, self.ϕ_c = μ_c, ϕ_z, ϕ_c
-        self.ρ, self.ρ_z, self.ρ_c, self.ρ_λ = ρ, ρ_z, ρ_c, ρ_λ
-        self.s_z, self.s_c, self.s_λ = s_z, s_c, s_λ
-        self.θ = (1 - γ) / (1 - 1 / ψ)
-        self.params = β, γ, ψ, μ_c, ρ, ϕ_z, ϕ_c, ρ_z, ρ_c, ρ_λ, s_z, s_c, s_λ
+class SSY(ParameterSet):
+    _TABLE = (
+        ("β", 0.999), ("γ", 8.89), ("ψ", 1.97),
+        ("ρ", 0.987), ("ρ_z", 0.992), ("ρ_c", 0.991), ("ρ_λ", 0.959),
+        ("s_z", math.sqrt(0.0039)), ("s_c", math.sqrt(0.0096)), ("s_λ", 0.0004),
+        ("μ_c", 0.0016),
+        ("φ_z", 0.215 * _SIGMA_BAR * math.sqrt(1 - 0.987 ** 2)),
+        ("φ_c", 1.00 * _SIGMA_BAR),
+    )
+    _PARAMS_ORDER = ("β", "γ", "ψ", "μ_c", "ρ", "φ_z", "φ_c", "ρ_z", "ρ_c", "ρ_λ", "s_z", "s_c", "s_λ")
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.θ = (1 - self.γ) / (1 - 1 / self.ψ)
 
 
 def wc_loglinear_factory(ssy):
-    """Constant terms of the log-linear approximation of the W/C ratio and a function that
-    evaluates it (log w) at a state (h_λ, h_c, h_z, z) -- mirror of ssy_model.py:86-156."""
+    """Constants of the log-linear approximation of the W/C ratio and a function evaluating it
+    (log w) at a state (h_λ, h_c, h_z, z): mirror of ssy_model.py:86-156."""
     from .loglinear import ssy_factory
     return ssy_factory(ssy)
