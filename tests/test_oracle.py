@@ -220,3 +220,35 @@ def test_anderson_oracle_converges_to_the_fixed_point():
     assert k < 10428                                 # fewer operator applications than plain iteration
     assert np.linalg.norm(op.T(w) - w) <= 1.5e-7
     np.testing.assert_allclose(w, w_sa, rtol=1e-7)
+
+
+def test_continuous_oracle_consistency():
+    """The continuous-state restatement (parity with the JAX original unpinned): quadrature rule
+    moments, interpolation exactness for multilinear functions, analytic JVP vs finite differences,
+    and agreement of the quadrature and a large Monte-Carlo rule."""
+    from oracle.continuous import ContSSY, qnwnorm, lin_interp, build_grid_ssy
+    nodes, weights = qnwnorm([5] * 4)
+    np.testing.assert_allclose(weights.sum(), 1.0, rtol=1e-14)
+    np.testing.assert_allclose(weights @ nodes, 0.0, atol=1e-14)
+    np.testing.assert_allclose(weights @ nodes ** 2, 1.0, rtol=1e-13)
+    np.testing.assert_allclose(weights @ nodes ** 4, 3.0, rtol=1e-13)
+    sizes = (3, 4, 5, 6)
+    grids = build_grid_ssy(O.SSY(), sizes)
+    mesh = np.meshgrid(*grids, indexing="ij")
+    f = 2.0 + 3e3 * mesh[0] - 1.5 * mesh[1] + 0.5 * mesh[2] * mesh[1] + 40 * mesh[3]      # multilinear
+    rng = np.random.default_rng(0)
+    pts = np.stack([rng.uniform(g[0], g[-1], 50) for g in grids])
+    exact = 2.0 + 3e3 * pts[0] - 1.5 * pts[1] + 0.5 * pts[2] * pts[1] + 40 * pts[3]
+    np.testing.assert_allclose(lin_interp(pts, f, grids), exact, rtol=1e-12)
+    far = np.stack([np.full(3, g[-1] + 10 * (g[-1] - g[0])) for g in grids])              # nearest-edge extension
+    np.testing.assert_allclose(lin_interp(far, f, grids), f[-1, -1, -1, -1], rtol=1e-14)
+    n3, w3 = qnwnorm([3] * 4)
+    op = ContSSY(O.SSY(), sizes, n3.T, w3)
+    w = 700 + 200 * rng.random(sizes)
+    v = rng.standard_normal(sizes)
+    h = 1e-3
+    fd = (op.T(w + h * v) - op.T(w - h * v)) / (2 * h)
+    np.testing.assert_allclose(op.jvp(w, v), fd, rtol=1e-7, atol=1e-9)
+    draws = rng.standard_normal((4, 20000))
+    mc = ContSSY(O.SSY(), sizes, draws, np.full(20000, 1 / 20000))
+    np.testing.assert_allclose(mc.T(w), op.T(w), rtol=2e-3)
