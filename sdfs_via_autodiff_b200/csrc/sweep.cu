@@ -68,17 +68,19 @@ __global__ void k_sweep_prologue(int64_t N, int64_t B, int64_t ldw, const double
 
 // One batched T step.  grid = tiles_m * tiles_b (m-major so consecutive CTAs reuse the same
 // rows of P out of L2).
+template <int TN>      // parameter columns per CTA tile: 128 (warp tile 32 x 64) or 64 (warp tile 32 x 32)
 __global__ void __launch_bounds__(GTHREADS, 1)
 k_sweep_gemm(const double *__restrict__ P, int64_t N, int64_t ldp, const double *__restrict__ V, int64_t B,
              int64_t ldw, const double *__restrict__ sig_c, const double *__restrict__ mz,
              SweepEpi ep, SweepCols sc, int tiles_b) {
     extern __shared__ __align__(16) double smem[];
     double *sA = smem;                                   // [GSTAGES][GM][GS]
-    double *sB = smem + (size_t)GSTAGES * GM * GS;       // [GSTAGES][GN][GS]
+    double *sB = smem + (size_t)GSTAGES * GM * GS;       // [GSTAGES][TN][GS]
+    constexpr int NJ = TN / 16;                          // 8x8 column blocks per warp
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1;             // 4 x 2 warps, warp tile 32 x 64
+    const int wm = warp >> 1, wn = warp & 1;             // 4 x 2 warps, warp tile 32 x (TN/2)
     const int tile_m = blockIdx.x / tiles_b, tile_b = blockIdx.x % tiles_b;
-    const int64_t m0 = (int64_t)tile_m * GM, b0 = (int64_t)tile_b * GN;
+    const int64_t m0 = (int64_t)tile_m * GM, b0 = (int64_t)tile_b * TN;
     const int64_t ksteps = (N + GK - 1) / GK;            // P and V are zero padded beyond N (ld multiple of 64)
 
     // loader mapping: 128 rows x 16 doubles = 128 x 8 chunks of 16 B per operand; 256 threads x 4 chunks
@@ -91,15 +93,16 @@ k_sweep_gemm(const double *__restrict__ P, int64_t N, int64_t ldp, const double 
             const int64_t n = m0 + row, b = b0 + row;
             const bool pa = n < N, pb = b < B;
             cp_async16(sA + ((size_t)stage * GM + row) * GS + seg * 2, P + (pa ? n : 0) * ldp + k0 + seg * 2, pa);
-            cp_async16(sB + ((size_t)stage * GN + row) * GS + seg * 2, V + (pb ? b : 0) * ldw + k0 + seg * 2, pb);
+            if (row < TN)
+                cp_async16(sB + ((size_t)stage * TN + row) * GS + seg * 2, V + (pb ? b : 0) * ldw + k0 + seg * 2, pb);
         }
     };
 
-    double acc[4][8][2];
+    double acc[4][NJ][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
     for (int s = 0; s < GSTAGES - 1; ++s) {
@@ -114,28 +117,28 @@ k_sweep_gemm(const double *__restrict__ P, int64_t N, int64_t ldp, const double 
         cp_async_commit();
         const int stage = (int)(ks % GSTAGES);
         const double *a_base = sA + ((size_t)stage * GM + wm * 32 + (lane >> 2)) * GS + (lane & 3);
-        const double *b_base = sB + ((size_t)stage * GN + wn * 64 + (lane >> 2)) * GS + (lane & 3);
+        const double *b_base = sB + ((size_t)stage * TN + wn * (TN / 2) + (lane >> 2)) * GS + (lane & 3);
 #pragma unroll
         for (int kk = 0; kk < GK; kk += 4) {
-            double af[4], bf[8];
+            double af[4], bf[NJ];
 #pragma unroll
             for (int i = 0; i < 4; ++i) af[i] = a_base[(size_t)i * 8 * GS + kk];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bf[j] = b_base[(size_t)j * 8 * GS + kk];
+            for (int j = 0; j < NJ; ++j) bf[j] = b_base[(size_t)j * 8 * GS + kk];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
     cp_async_wait<0>();
 
-    // epilogue: thread holds S[n = m0 + wm*32 + i*8 + lane/4][b = b0 + wn*64 + j*8 + 2*(lane%4) + {0,1}]
+    // epilogue: thread holds S[n = m0 + wm*32 + i*8 + lane/4][b = b0 + wn*(TN/2) + j*8 + 2*(lane%4) + {0,1}]
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NJ; ++j) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int64_t b = b0 + wn * 64 + j * 8 + 2 * (lane & 3) + h;
+            const int64_t b = b0 + wn * (TN / 2) + j * 8 + 2 * (lane & 3) + h;
             double emax = 0.0;
             if (b < B) {
                 if (ep.mode == 2) {
@@ -283,12 +286,25 @@ static int sweep_setup(sdfs_op *op, const double *h_prefs, int64_t B, bool panel
 static int sweep_gemm(sdfs_op *op, SweepWork &w, int64_t B, const double *V, const SweepEpi &ep, const SweepCols &sc) {
     sdfs_ctx *ctx = op->ctx;
     const int64_t N = op->dv.N;
-    const int tiles_m = (int)((N + GM - 1) / GM), tiles_b = (int)((B + GN - 1) / GN);
-    const size_t smem = (size_t)GSTAGES * (GM + GN) * GS * sizeof(double);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles_m = (int)((N + GM - 1) / GM);
+    // column-tile width: 128 unless 64 fills the last wave of CTAs markedly better (one CTA per SM;
+    // a 64-wide tile does half the work of a 128-wide one at ~90 % of its per-tile efficiency)
+    auto wave_eff = [&](int tn) {
+        const double tiles = (double)tiles_m * (double)((B + tn - 1) / tn);
+        return tiles / (ceil(tiles / ctx->sm_count) * ctx->sm_count);
+    };
+    const int tn = (0.9 * wave_eff(64) > wave_eff(128)) ? 64 : 128;
+    const int tiles_b = (int)((B + tn - 1) / tn);
+    const size_t smem = (size_t)GSTAGES * (GM + tn) * GS * sizeof(double);
     const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
     if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
-    k_sweep_gemm<<<tiles_m * tiles_b, GTHREADS, smem, ctx->stream>>>(op->dv.P, N, op->dv.ld, V, B, w.ldw, w.sc, w.mz, ep, sc, tiles_b);
+    if (tn == 128) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_gemm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_sweep_gemm<128><<<tiles_m * tiles_b, GTHREADS, smem, ctx->stream>>>(op->dv.P, N, op->dv.ld, V, B, w.ldw, w.sc, w.mz, ep, sc, tiles_b);
+    } else {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_gemm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_sweep_gemm<64><<<tiles_m * tiles_b, GTHREADS, smem, ctx->stream>>>(op->dv.P, N, op->dv.ld, V, B, w.ldw, w.sc, w.mz, ep, sc, tiles_b);
+    }
     if (prof) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
         ctx->prof_used += 2;
