@@ -188,6 +188,18 @@ __device__ __forceinline__ double ld_stream1(const double *p) {
     return r;
 }
 
+// x^e for x > 0 through exp(e log x): about half the latency of pow() (tools/lat_probe.cu: 443 vs
+// 844 cycles).  Relative error <= ~|e log x| ulp (<= 1e-13 for the calibrations used), which the
+// 1/theta power of T shrinks again by |theta|; NaN for x < 0 and inf for x = 0, e < 0 like pow.
+__device__ __forceinline__ double pow_pos(double x, double e) { return exp(e * log(x)); }
+
+// fp64 tensor-core tile: D(8x8) += A(8x4, row) B(4x8, col).  Lane l holds A[l/4][l%4], B[l%4][l/4]
+// and D[l/4][2(l%4) + {0,1}].  (tcgen05 has no f64 kind; DMMA is the fp64 tensor path on sm_100a.)
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 // Coherent (weak, L1-cacheable) loads of the matvec input x.  x is rewritten between
 // grid barriers inside the persistent loop kernels, so it must never be turned
 // into a non-coherent ld.global.nc by the compiler.

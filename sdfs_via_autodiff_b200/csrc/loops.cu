@@ -263,8 +263,8 @@ struct KronLoopOp {
     __device__ __forceinline__ double beta() const { return kv.beta; }
     __device__ __forceinline__ double theta() const { return kv.theta; }
     static constexpr bool kNeedsW = false;
-    __device__ __forceinline__ double stage_T(int64_t n, double w) const { return kv.a_col[n] * pow(w, kv.theta); }
-    __device__ __forceinline__ double stage_c(int64_t n, double w) const { return kv.a_col[n] * pow(w, kv.theta - 1.0); }
+    __device__ __forceinline__ double stage_T(int64_t n, double w) const { return kv.a_col[n] * pow_pos(w, kv.theta); }
+    __device__ __forceinline__ double stage_c(int64_t n, double w) const { return kv.a_col[n] * pow_pos(w, kv.theta - 1.0); }
     __device__ __forceinline__ double rowfac(int64_t n) const { return kv.a_row[n]; }
     template <class Epi>
     __device__ __forceinline__ bool apply_T(cg::grid_group &grid, const LoopEnv &env, unsigned long long &epoch,

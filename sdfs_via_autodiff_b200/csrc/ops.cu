@@ -18,17 +18,18 @@ int comm_allgather_rows(sdfs_ctx *ctx, double *d_vec, int64_t N);   // comm.cu
 // mode 1: x0 = a_col * w^theta, x1 = a_col * w^(theta-1) * v   (fused T + JVP)
 // mode 2: x0 = a_col * w^theta, x1 = a_col * w^(theta-1)       (SDF)
 // mode 3: x = v                                     (plain P x; stages into the aligned buffer)
+template <bool FAST>   // FAST: exp(e log x) power form (factor-form path, where the N pows are a visible cost)
 __global__ void k_prologue(int mode, int64_t N, const double *__restrict__ a_col, const double *__restrict__ w,
                            const double *__restrict__ v, double theta, double *__restrict__ x0,
                            double *__restrict__ x1) {
     for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
         if (mode == 3) { x0[n] = v[n]; continue; }
         const double wn = w[n];
-        const double wt = pow(wn, theta);
+        const double wt = FAST ? pow_pos(wn, theta) : pow(wn, theta);
         const double ac = a_col[n];
         x0[n] = ac * wt;
-        if (mode == 1) x1[n] = ac * pow(wn, theta - 1.0) * v[n];
-        else if (mode == 2) x1[n] = ac * pow(wn, theta - 1.0);
+        if (mode == 1) x1[n] = ac * (wt / wn) * v[n];          // w^(theta-1) = w^theta / w
+        else if (mode == 2) x1[n] = ac * (wt / wn);
     }
 }
 
@@ -44,20 +45,29 @@ struct EpiArgs {
     double *out0, *out1;
 };
 
+template <bool FAST = false>
 __device__ __forceinline__ void apply_epilogue(const EpiArgs &e, int64_t n, double s0, double s1) {
+    auto pw = [](double x, double ex) { return FAST ? pow_pos(x, ex) : pow(x, ex); };
     if (e.mode == 0) {
-        e.out0[n] = 1.0 + e.beta * pow(e.a_row[n] * s0, 1.0 / e.theta);
+        e.out0[n] = 1.0 + e.beta * pw(e.a_row[n] * s0, 1.0 / e.theta);
     } else if (e.mode == 1) {
         const double ar = e.a_row[n];
-        e.out0[n] = e.beta * pow(ar * s0, (1.0 - e.theta) / e.theta) * ar * s1;
+        e.out0[n] = e.beta * pw(ar * s0, (1.0 - e.theta) / e.theta) * ar * s1;
     } else if (e.mode == 2) {
         const double bt = pow(e.beta, e.theta);
         const double wm1 = e.w[n] - 1.0;
-        if (e.out0) e.out0[n] = bt * e.e_sdf[n] * pow(wm1, 1.0 - e.theta) * s1;
-        if (e.out1) e.out1[n] = bt * (e.a_row[n] * s0) / pow(wm1, e.theta) - 1.0;
+        if (e.out0) e.out0[n] = bt * e.e_sdf[n] * pw(wm1, 1.0 - e.theta) * s1;
+        if (e.out1) e.out1[n] = bt * (e.a_row[n] * s0) / pw(wm1, e.theta) - 1.0;
     } else {
         e.out0[n] = s0;
     }
+}
+
+// elementwise epilogue at full occupancy (factor-form path: the contraction kernels run at 8-12
+// warps per SM, far too few to hide the latency of one pow per output)
+__global__ void k_epilogue_ew(int64_t N, const double *__restrict__ s0, const double *__restrict__ s1, EpiArgs e) {
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x)
+        apply_epilogue<true>(e, n, s0[n], s1 ? s1[n] : s0[n]);
 }
 
 template <int NX>
@@ -67,7 +77,7 @@ k_dense_apply(const __grid_constant__ DenseView dv, const double *x0, const doub
     RowPipe<NX> *rp = reinterpret_cast<RowPipe<NX> *>(dyn_smem);
     PipeState st;
     if (dv.vec2) pipe_init(rp, st);
-    dense_pass<NX>(dv, x0, x1, rp, st, [&](int64_t n, double s0, double s1) { apply_epilogue(e, n, s0, s1); });
+    dense_pass<NX>(dv, x0, x1, rp, st, [&](int64_t n, double s0, double s1) { apply_epilogue<false>(e, n, s0, s1); });
 }
 
 __global__ void __launch_bounds__(256) k_kron_mode(KronView kv, int m, const double *__restrict__ in, double *__restrict__ out) {
@@ -80,8 +90,8 @@ __global__ void __launch_bounds__(256) k_kron_last(KronView kv, int m, const dou
                                                    const double *__restrict__ s0_done, EpiArgs e) {
     __shared__ __align__(16) double smat[KRON_SMAT_DOUBLES];
     kron_mode_apply(kv, m, in, smat, [&](int64_t idx, double s) {
-        if (s0_done) apply_epilogue(e, idx, s0_done[idx], s);
-        else apply_epilogue(e, idx, s, s);
+        if (s0_done) apply_epilogue<true>(e, idx, s0_done[idx], s);
+        else apply_epilogue<true>(e, idx, s, s);
     });
 }
 
@@ -235,7 +245,8 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
     const int nx = (pmode == 1 || pmode == 2) ? 2 : 1;
     const double *a_col = dense ? op->dv.a_col : op->kv.a_col;
     const double theta = dense ? op->dv.theta : op->kv.theta;
-    k_prologue<<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(pmode, N, a_col, d_w, d_v, theta, x0, x1);
+    if (dense) k_prologue<false><<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(pmode, N, a_col, d_w, d_v, theta, x0, x1);
+    else k_prologue<true><<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(pmode, N, a_col, d_w, d_v, theta, x0, x1);
     ctx->launches++;
     if (dense) {
         if (op->dv.row_end > op->dv.row_begin) {
@@ -254,28 +265,26 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)N * sizeof(double)));
         }
         // work items of the fibre kernel are distributed round-robin: any grid size is valid
-        const int grid = ctx->sm_count * 4;
-        double *s0_done = nullptr;
+        const int grid = ctx->sm_count * 6;
+        double *sfin[2] = {op->work + 2 * op->ldv, op->work + 3 * op->ldv};     // finished contractions
         for (int pass = 0; pass < nx; ++pass) {
             const double *in = (pass == 0) ? x0 : x1;
-            // pass 0 of a two-vector apply finishes s0 into work[2]; the last pass feeds the epilogue
-            const bool last_vec = (pass == nx - 1);
             for (int m = 0; m < kv.n_modes; ++m) {
                 const bool last_mode = (m == kv.n_modes - 1);
-                // few fibres (small grids): narrower CTAs give more work items to spread over the SMs
-                const int64_t fibres = N / kv.shape[kv.modes[m].dim];
-                const int threads = fibres >= (int64_t)ctx->sm_count * 512 ? 256 : (fibres >= (int64_t)ctx->sm_count * 128 ? 128 : 64);
-                if (last_mode && last_vec) {
-                    k_kron_last<<<grid, threads, 0, ctx->stream>>>(kv, m, in, s0_done, e);
-                } else {
-                    double *out = last_mode ? (op->work + 2 * op->ldv) : op->kron_tmp[m & 1];
-                    k_kron_mode<<<grid, threads, 0, ctx->stream>>>(kv, m, in, out);
-                    in = out;
-                    if (last_mode) s0_done = out;
-                }
+                // tensor-core contraction (n >= 12): 8 warps per CTA, each on tiles of 8 fibres;
+                // register-tiled FMA contraction (short axes): one fibre per thread
+                const int nm = kv.shape[kv.modes[m].dim];
+                const int64_t fibres = N / nm;
+                const int threads = (nm >= 12 && nm <= KRON_NMAX_LIMIT) ? 256
+                                    : (fibres >= (int64_t)ctx->sm_count * 128 ? 128 : 64);
+                double *out = last_mode ? sfin[pass] : op->kron_tmp[m & 1];
+                k_kron_mode<<<grid, threads, 0, ctx->stream>>>(kv, m, in, out);
+                in = out;
                 ctx->launches++;
             }
         }
+        k_epilogue_ew<<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(N, sfin[0], nx > 1 ? sfin[1] : nullptr, e);
+        ctx->launches++;
         CUDA_TRY(ctx, cudaGetLastError());
     }
     return SDFS_OK;

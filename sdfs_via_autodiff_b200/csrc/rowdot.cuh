@@ -435,14 +435,103 @@ __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const
     }
 }
 
-// dispatch on the size of the contracted axis; falls back to the cached-load pass for n > 64
+// ---------------------------------------------------------------------------
+// Tensor-core mode contraction (DMMA m8n8k4) for 12 <= n <= 64.
+// One mode is the GEMM  out[f, i] = sum_k in[f, k] M[i, k]  over the fibres f that share the factor
+// matrix M (n x n).  A warp owns a tile of 8 fibres: the A fragments are the fibre values themselves
+// (lane l holds in[fibre l/4][k0 + l%4], read straight from global: for the innermost axis that is
+// 32 contiguous bytes per fibre, for the other axes 64 contiguous bytes per k, so every sector fetched
+// is fully used), the B fragments come from the matrix staged in shared memory with row pitch
+// NMAX + 4 (= 4 mod 8 doubles: the 8 x 4 fragment read is bank-conflict free), and the
+// ceil(n/8) accumulator tiles stay in registers.  Per fibre tile: ceil(n/4) loads, ceil(n/4) ceil(n/8)
+// DMMAs and as many 8-byte LDS, 2 ceil(n/8) stores - against n^2/2 LDS.128 and n^2 DFMA per fibre
+// in kron_mode_fibre, whose shared-memory pipe saturates at ~27 % of the fp64 rate.
+// A work item = (matrix-axes combination, chunk of 256 fibres - 64 when that would leave CTAs
+// idle); the matrix is re-staged only when it changes between consecutive items of a CTA.
+// ---------------------------------------------------------------------------
+#define KRON_CHUNK 256
+template <int NMAX, class Sink>
+__device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const double *in, double *smat, Sink &&sink) {
+    constexpr int PITCH = NMAX + 4, KT = NMAX / 4, IT = NMAX / 8;
+    const KronMode &md = kv.modes[m];
+    const int n = kv.shape[md.dim];
+    const int kt_n = (n + 3) >> 2, it_n = (n + 7) >> 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int CH = (md.Mcount * ((md.Fcount + KRON_CHUNK - 1) / KRON_CHUNK) >= 2LL * gridDim.x) ? KRON_CHUNK : 64;
+    const long long chunks = (md.Fcount + CH - 1) / CH;
+    const long long items = md.Mcount * chunks;
+    int cur_mat = -1;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long mc = item / chunks, chunk = item - mc * chunks;
+        long long rem = mc, mbase = 0;
+        int mat = 0;
+        for (int a = md.nM - 1; a >= 0; --a) {
+            const int c = (int)(rem % md.Mshape[a]);
+            rem /= md.Mshape[a];
+            mat += c * md.Mmat[a];
+            mbase += c * md.Mstride[a];
+        }
+        if (mat != cur_mat) {                   // uniform over the CTA
+            __syncthreads();                    // previous matrix no longer in use
+            const double *msrc = md.mat + (long long)mat * n * n;
+            for (int e = threadIdx.x; e < it_n * 8 * PITCH; e += blockDim.x) {
+                const int i = e / PITCH, j = e - i * PITCH;
+                smat[e] = (i < n && j < n) ? msrc[i * n + j] : 0.0;
+            }
+            __syncthreads();
+            cur_mat = mat;
+        }
+        for (int t = warp; t < CH / 8; t += nwarps) {
+            const long long f0 = chunk * CH + t * 8;
+            if (f0 >= md.Fcount) break;
+            const long long f = f0 + g;
+            const bool fv = f < md.Fcount;
+            long long r2 = fv ? f : 0, base = mbase;
+            for (int a = md.nF - 1; a >= 0; --a) {
+                const int c = (int)(r2 % md.Fshape[a]);
+                r2 /= md.Fshape[a];
+                base += c * md.Fstride[a];
+            }
+            double a[KT];
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                const int k = kt * 4 + q;
+                a[kt] = (fv && k < n) ? in[base + k * md.stride] : 0.0;
+            }
+            double c[IT][2];
+#pragma unroll
+            for (int it = 0; it < IT; ++it) c[it][0] = c[it][1] = 0.0;
+            const double *brow = smat + g * PITCH + q;
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                if (kt < kt_n) {
+#pragma unroll
+                    for (int it = 0; it < IT; ++it)
+                        if (it < it_n) dmma884(c[it][0], c[it][1], a[kt], brow[it * 8 * PITCH + kt * 4]);
+                }
+            }
+            if (fv) {
+#pragma unroll
+                for (int it = 0; it < IT; ++it) {
+                    const int i = it * 8 + 2 * q;
+                    if (i < n) sink(base + i * md.stride, c[it][0]);
+                    if (i + 1 < n) sink(base + (i + 1) * md.stride, c[it][1]);
+                }
+            }
+        }
+    }
+}
+
+// dispatch on the size of the contracted axis: register-tiled FMA kernel for short axes, the
+// tensor-core contraction up to 64, the cached-load pass beyond
 template <class Sink>
 __device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const double *in, double *smat, Sink &&sink) {
     const int n = kv.shape[kv.modes[m].dim];
     if (n <= 8) kron_mode_fibre<8>(kv, m, in, smat, sink);
-    else if (n <= 16) kron_mode_fibre<16>(kv, m, in, smat, sink);
-    else if (n <= 32) kron_mode_fibre<32>(kv, m, in, smat, sink);
-    else if (n <= KRON_NMAX_LIMIT) kron_mode_fibre<64>(kv, m, in, smat, sink);
+    else if (n < 12) kron_mode_fibre<16>(kv, m, in, smat, sink);
+    else if (n <= 32) kron_mode_dmma<32>(kv, m, in, smat, sink);
+    else if (n <= KRON_NMAX_LIMIT) kron_mode_dmma<64>(kv, m, in, smat, sink);
     else kron_mode_pass(kv, m, in, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, sink);
 }
-#define KRON_SMAT_DOUBLES (KRON_NMAX_LIMIT * KRON_NMAX_LIMIT)
+#define KRON_SMAT_DOUBLES (KRON_NMAX_LIMIT * (KRON_NMAX_LIMIT + 4))

@@ -50,11 +50,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
-
 // V[b][k] = exp(theta_b * h_lam[k]) * W[b][k]^theta_b   (prologue; N*B elements)
 __global__ void k_sweep_prologue(int64_t N, int64_t B, int64_t ldw, const double *__restrict__ h_lam,
                                  const double *__restrict__ W, SweepCols sc, double *__restrict__ V) {

@@ -622,3 +622,36 @@ def test_full_size_properties(model, shapes):
     assert np.linalg.norm(np.asarray(d(wk)) - wkn) <= 1.05e-4
     assert np.linalg.norm(kop.T(wkn) - wkn) <= 1.05e-4
     del d, k
+
+
+@pytest.mark.parametrize("model,shapes", [("ssy", (13, 5, 33, 20)), ("ssy", (9, 40, 12, 7)),
+                                          ("gcy", (14, 3, 5, 17, 2, 12)), ("gcy", (2, 13, 3, 2, 37, 3))])
+def test_factor_form_ragged_axes_tensor_core_modes(model, shapes):
+    """Factor-form contraction across its three code paths in one operator (short axes: FMA
+    kernel; 12..32 and 33..64: DMMA tiles with ragged fibre tiles, padded k and i tiles):
+    T, JVP, SA and Newton loops against the oracle's einsum form."""
+    if model == "ssy":
+        mdl = O.SSY()
+        arrays = O.discretize_ssy(mdl, shapes)
+        kop = O.KronSSY(shapes, mdl.params, arrays)
+        op = S.make_T_ssy(mdl, shapes, arrays, storage="kron")
+    else:
+        mdl = O.GCY()
+        arrays = O.discretize_gcy(mdl, shapes)
+        kop = O.KronGCY(shapes, mdl.params, arrays)
+        op = S.make_T_gcy(mdl, shapes, arrays, storage="kron")
+    rng = np.random.default_rng(77)
+    w = 500 + 400 * rng.random(shapes)
+    v = rng.standard_normal(shapes)
+    np.testing.assert_allclose(np.asarray(op(w)), kop.T(w), rtol=RTOL_T)
+    np.testing.assert_allclose(np.asarray(op.jvp(w, v)), kop.jvp(w, v), rtol=1e-10, atol=1e-11)
+    # 25 SA steps inside the persistent loop kernel == 25 oracle steps
+    ws, k = S.successive_approx(op, w, tol=0.0, max_iter=25, verbose=False)
+    ref = w.copy()
+    for _ in range(25):
+        ref = kop.T(ref)
+    assert k == 25
+    np.testing.assert_allclose(np.asarray(ws), ref, rtol=1e-11)
+    wn, _ = S.newton_solver(op, np.full(shapes, 800.0), tol=1e-9, bicgstab_atol=1e-10, verbose=False)
+    wn = np.asarray(wn)
+    assert np.max(np.abs(kop.T(wn) - wn)) < 1e-6 * np.max(wn)
