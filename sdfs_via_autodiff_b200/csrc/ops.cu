@@ -43,16 +43,17 @@ struct EpiArgs {
     const double *a_row, *e_sdf, *w;
     double beta, theta;
     double *out0, *out1;
+    double inv_theta = 0.0;     // 1 / theta, filled by the launchers
 };
 
 template <bool FAST = false>
 __device__ __forceinline__ void apply_epilogue(const EpiArgs &e, int64_t n, double s0, double s1) {
     auto pw = [](double x, double ex) { return FAST ? pow_pos(x, ex) : pow(x, ex); };
     if (e.mode == 0) {
-        e.out0[n] = 1.0 + e.beta * pw(e.a_row[n] * s0, 1.0 / e.theta);
+        e.out0[n] = 1.0 + e.beta * pw(e.a_row[n] * s0, e.inv_theta);
     } else if (e.mode == 1) {
         const double ar = e.a_row[n];
-        e.out0[n] = e.beta * pw(ar * s0, (1.0 - e.theta) / e.theta) * ar * s1;
+        e.out0[n] = e.beta * pw(ar * s0, e.inv_theta - 1.0) * ar * s1;
     } else if (e.mode == 2) {
         const double bt = pow(e.beta, e.theta);
         const double wm1 = e.w[n] - 1.0;
@@ -82,19 +83,8 @@ k_dense_apply(const __grid_constant__ DenseView dv, const double *x0, const doub
 
 __global__ void __launch_bounds__(256) k_kron_mode(KronView kv, int m, const double *__restrict__ in, double *__restrict__ out) {
     __shared__ __align__(16) double smat[KRON_SMAT_DOUBLES];
-    kron_mode_apply(kv, m, in, smat, [&](int64_t idx, double s) { out[idx] = s; });
+    kron_mode_apply<true>(kv, m, in, smat, [&](int64_t idx, double s) { out[idx] = s; });
 }
-// last mode of a two-vector apply: tmpA holds the finished s0 (or unused), the
-// contraction of `in` gives s1 (NX = 2) or s0 (NX = 1)
-__global__ void __launch_bounds__(256) k_kron_last(KronView kv, int m, const double *__restrict__ in,
-                                                   const double *__restrict__ s0_done, EpiArgs e) {
-    __shared__ __align__(16) double smat[KRON_SMAT_DOUBLES];
-    kron_mode_apply(kv, m, in, smat, [&](int64_t idx, double s) {
-        if (s0_done) apply_epilogue<true>(e, idx, s0_done[idx], s);
-        else apply_epilogue<true>(e, idx, s, s);
-    });
-}
-
 // 2-D TMA descriptor of the local row slice of P: dims (N columns, nloc rows), row pitch ld,
 // box 256 columns x 8 rows, zero fill outside the matrix.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -240,6 +230,7 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const bool dense = op->storage == SDFS_STORAGE_DENSE;
     const int64_t N = dense ? op->dv.N : op->kv.N;
+    e.inv_theta = 1.0 / e.theta;
     TRY(op_ensure_work(op, 4));
     double *x0 = op->work, *x1 = op->work + op->ldv;
     const int nx = (pmode == 1 || pmode == 2) ? 2 : 1;
@@ -265,7 +256,8 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)N * sizeof(double)));
         }
         // work items of the fibre kernel are distributed round-robin: any grid size is valid
-        const int grid = ctx->sm_count * 6;
+        static const int kron_tc_threads = getenv("SDFS_KRON_THREADS") ? atoi(getenv("SDFS_KRON_THREADS")) : 256;
+        static const int kron_tc_ctas = getenv("SDFS_KRON_CTAS") ? atoi(getenv("SDFS_KRON_CTAS")) : 2;
         double *sfin[2] = {op->work + 2 * op->ldv, op->work + 3 * op->ldv};     // finished contractions
         for (int pass = 0; pass < nx; ++pass) {
             const double *in = (pass == 0) ? x0 : x1;
@@ -275,8 +267,9 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
                 // register-tiled FMA contraction (short axes): one fibre per thread
                 const int nm = kv.shape[kv.modes[m].dim];
                 const int64_t fibres = N / nm;
-                const int threads = (nm >= 12 && nm <= KRON_NMAX_LIMIT) ? 256
-                                    : (fibres >= (int64_t)ctx->sm_count * 128 ? 128 : 64);
+                const bool tc = nm >= 12 && nm <= KRON_NMAX_LIMIT;
+                const int threads = tc ? kron_tc_threads : (fibres >= (int64_t)ctx->sm_count * 128 ? 128 : 64);
+                const int grid = tc ? ctx->sm_count * kron_tc_ctas : ctx->sm_count * 6;
                 double *out = last_mode ? sfin[pass] : op->kron_tmp[m & 1];
                 k_kron_mode<<<grid, threads, 0, ctx->stream>>>(kv, m, in, out);
                 in = out;
@@ -538,6 +531,7 @@ int sdfs_op_bench_pass(sdfs_op *op, int mode, int reps, double *avg_ms) {
     TRY(op_ensure_work(op, 4));
     double *x0 = op->work, *scratch = op->work + 3 * op->ldv;
     EpiArgs e{mode, op->dv.a_row, nullptr, nullptr, op->dv.beta, op->dv.theta, scratch, nullptr};
+    e.inv_theta = 1.0 / e.theta;
     TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     for (int i = 0; i < reps; ++i) TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e));

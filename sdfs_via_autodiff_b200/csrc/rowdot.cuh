@@ -446,11 +446,13 @@ __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const
 // ceil(n/8) accumulator tiles stay in registers.  Per fibre tile: ceil(n/4) loads, ceil(n/4) ceil(n/8)
 // DMMAs and as many 8-byte LDS, 2 ceil(n/8) stores - against n^2/2 LDS.128 and n^2 DFMA per fibre
 // in kron_mode_fibre, whose shared-memory pipe saturates at ~27 % of the fp64 rate.
-// A work item = (matrix-axes combination, chunk of 256 fibres - 64 when that would leave CTAs
-// idle); the matrix is re-staged only when it changes between consecutive items of a CTA.
+// Work distribution: the tiles (matrix-axes combination major, fibre tile minor) are split into one
+// contiguous range per CTA, so a CTA re-stages the matrix only when its range crosses into the next
+// combination, and every CTA gets the same number of tiles (+-1) whatever the grid.  Inside a
+// range the warps take tiles round-robin and prefetch the next tile's fragments before the DMMAs
+// of the current one.
 // ---------------------------------------------------------------------------
-#define KRON_CHUNK 256
-template <int NMAX, class Sink>
+template <int NMAX, bool PREFETCH, class Sink>
 __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const double *in, double *smat, Sink &&sink) {
     constexpr int PITCH = NMAX + 4, KT = NMAX / 4, IT = NMAX / 8;
     const KronMode &md = kv.modes[m];
@@ -458,12 +460,14 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const 
     const int kt_n = (n + 3) >> 2, it_n = (n + 7) >> 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const int CH = (md.Mcount * ((md.Fcount + KRON_CHUNK - 1) / KRON_CHUNK) >= 2LL * gridDim.x) ? KRON_CHUNK : 64;
-    const long long chunks = (md.Fcount + CH - 1) / CH;
-    const long long items = md.Mcount * chunks;
+    const long long tpm = (md.Fcount + 7) >> 3;              // fibre tiles per matrix combination
+    const long long T = md.Mcount * tpm;
+    const long long t_begin = T * blockIdx.x / gridDim.x, t_end = T * (blockIdx.x + 1) / gridDim.x;
+    const long long kstride = md.stride;
     int cur_mat = -1;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-        const long long mc = item / chunks, chunk = item - mc * chunks;
+    for (long long seg = t_begin; seg < t_end;) {
+        const long long mc = seg / tpm;
+        const long long seg_end = (mc + 1) * tpm < t_end ? (mc + 1) * tpm : t_end;
         long long rem = mc, mbase = 0;
         int mat = 0;
         for (int a = md.nM - 1; a >= 0; --a) {
@@ -482,27 +486,43 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const 
             __syncthreads();
             cur_mat = mat;
         }
-        for (int t = warp; t < CH / 8; t += nwarps) {
-            const long long f0 = chunk * CH + t * 8;
-            if (f0 >= md.Fcount) break;
-            const long long f = f0 + g;
-            const bool fv = f < md.Fcount;
-            long long r2 = fv ? f : 0, base = mbase;
-            for (int a = md.nF - 1; a >= 0; --a) {
-                const int c = (int)(r2 % md.Fshape[a]);
-                r2 /= md.Fshape[a];
-                base += c * md.Fstride[a];
+        // fragment loader: lane (g, q) reads fibre 8 t + g at k = 4 kt + q
+        auto load_tile = [&](long long t, double (&a)[KT], long long &base, bool &fv) {
+            const long long f = (t - mc * tpm) * 8 + g;
+            fv = f < md.Fcount;
+            long long r2 = fv ? f : 0;
+            base = mbase;
+            for (int ax = md.nF - 1; ax >= 0; --ax) {
+                const int c = (int)(r2 % md.Fshape[ax]);
+                r2 /= md.Fshape[ax];
+                base += c * md.Fstride[ax];
             }
-            double a[KT];
 #pragma unroll
             for (int kt = 0; kt < KT; ++kt) {
                 const int k = kt * 4 + q;
-                a[kt] = (fv && k < n) ? in[base + k * md.stride] : 0.0;
+                a[kt] = (fv && k < n) ? in[base + k * kstride] : 0.0;
+            }
+        };
+        long long t = seg + warp;
+        double a[KT];
+        long long base = 0;
+        bool fv = false;
+        if (PREFETCH && t < seg_end) load_tile(t, a, base, fv);
+        const double *brow = smat + g * PITCH + q;
+        while (t < seg_end) {
+            double an[KT];
+            long long bn = 0;
+            bool vn = false;
+            const long long tn = t + nwarps;
+            if (!PREFETCH) load_tile(t, a, base, fv);
+            if (PREFETCH && tn < seg_end) load_tile(tn, an, bn, vn);
+            else if (PREFETCH) {
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) an[kt] = 0.0;
             }
             double c[IT][2];
 #pragma unroll
             for (int it = 0; it < IT; ++it) c[it][0] = c[it][1] = 0.0;
-            const double *brow = smat + g * PITCH + q;
 #pragma unroll
             for (int kt = 0; kt < KT; ++kt) {
                 if (kt < kt_n) {
@@ -515,23 +535,32 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const 
 #pragma unroll
                 for (int it = 0; it < IT; ++it) {
                     const int i = it * 8 + 2 * q;
-                    if (i < n) sink(base + i * md.stride, c[it][0]);
-                    if (i + 1 < n) sink(base + (i + 1) * md.stride, c[it][1]);
+                    if (i < n) sink(base + i * kstride, c[it][0]);
+                    if (i + 1 < n) sink(base + (i + 1) * kstride, c[it][1]);
                 }
             }
+            if (PREFETCH) {
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) a[kt] = an[kt];
+                base = bn; fv = vn;
+            }
+            t = tn;
         }
+        seg = seg_end;
     }
 }
 
 // dispatch on the size of the contracted axis: register-tiled FMA kernel for short axes, the
 // tensor-core contraction up to 64, the cached-load pass beyond
-template <class Sink>
+// (PREFETCH: software-pipelined fragment loads, +32 registers - for the stand-alone mode kernels;
+// the persistent loop kernels keep the lean variant)
+template <bool PREFETCH = false, class Sink>
 __device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const double *in, double *smat, Sink &&sink) {
     const int n = kv.shape[kv.modes[m].dim];
     if (n <= 8) kron_mode_fibre<8>(kv, m, in, smat, sink);
     else if (n < 12) kron_mode_fibre<16>(kv, m, in, smat, sink);
-    else if (n <= 32) kron_mode_dmma<32>(kv, m, in, smat, sink);
-    else if (n <= KRON_NMAX_LIMIT) kron_mode_dmma<64>(kv, m, in, smat, sink);
+    else if (n <= 32) kron_mode_dmma<32, PREFETCH>(kv, m, in, smat, sink);
+    else if (n <= KRON_NMAX_LIMIT) kron_mode_dmma<64, PREFETCH>(kv, m, in, smat, sink);
     else kron_mode_pass(kv, m, in, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, sink);
 }
 #define KRON_SMAT_DOUBLES (KRON_NMAX_LIMIT * (KRON_NMAX_LIMIT + 4))
