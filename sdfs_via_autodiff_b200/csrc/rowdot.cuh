@@ -452,18 +452,19 @@ __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const
 // range the warps take tiles round-robin and prefetch the next tile's fragments before the DMMAs
 // of the current one.
 // ---------------------------------------------------------------------------
-template <int NMAX, bool PREFETCH, class Sink>
+template <int IT /* 8-row output tiles */, bool PREFETCH, class Sink>
 __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const double *in, double *smat, Sink &&sink) {
-    constexpr int PITCH = NMAX + 4, KT = NMAX / 4, IT = NMAX / 8;
+    constexpr int PITCH = 8 * IT + 4, KT = 2 * IT;          // n <= 8 IT  =>  ceil(n/4) <= 2 IT
     const KronMode &md = kv.modes[m];
     const int n = kv.shape[md.dim];
-    const int kt_n = (n + 3) >> 2, it_n = (n + 7) >> 3;
+    const int kt_n = (n + 3) >> 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const long long tpm = (md.Fcount + 7) >> 3;              // fibre tiles per matrix combination
     const long long T = md.Mcount * tpm;
     const long long t_begin = T * blockIdx.x / gridDim.x, t_end = T * (blockIdx.x + 1) / gridDim.x;
     const long long kstride = md.stride;
+    const bool small_f = md.Fcount < (1LL << 31);            // 32-bit index decode (always, in practice)
     int cur_mat = -1;
     for (long long seg = t_begin; seg < t_end;) {
         const long long mc = seg / tpm;
@@ -479,7 +480,7 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const 
         if (mat != cur_mat) {                   // uniform over the CTA
             __syncthreads();                    // previous matrix no longer in use
             const double *msrc = md.mat + (long long)mat * n * n;
-            for (int e = threadIdx.x; e < it_n * 8 * PITCH; e += blockDim.x) {
+            for (int e = threadIdx.x; e < IT * 8 * PITCH; e += blockDim.x) {
                 const int i = e / PITCH, j = e - i * PITCH;
                 smat[e] = (i < n && j < n) ? msrc[i * n + j] : 0.0;
             }
@@ -490,17 +491,27 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const 
         auto load_tile = [&](long long t, double (&a)[KT], long long &base, bool &fv) {
             const long long f = (t - mc * tpm) * 8 + g;
             fv = f < md.Fcount;
-            long long r2 = fv ? f : 0;
             base = mbase;
-            for (int ax = md.nF - 1; ax >= 0; --ax) {
-                const int c = (int)(r2 % md.Fshape[ax]);
-                r2 /= md.Fshape[ax];
-                base += c * md.Fstride[ax];
+            if (small_f) {
+                unsigned r2 = fv ? (unsigned)f : 0u;
+                for (int ax = md.nF - 1; ax >= 0; --ax) {
+                    const unsigned sh = (unsigned)md.Fshape[ax], qd = r2 / sh;
+                    base += (long long)(r2 - qd * sh) * md.Fstride[ax];
+                    r2 = qd;
+                }
+            } else {
+                long long r2 = fv ? f : 0;
+                for (int ax = md.nF - 1; ax >= 0; --ax) {
+                    const int c = (int)(r2 % md.Fshape[ax]);
+                    r2 /= md.Fshape[ax];
+                    base += c * md.Fstride[ax];
+                }
             }
+            const double *p = in + base + q * kstride;
 #pragma unroll
             for (int kt = 0; kt < KT; ++kt) {
-                const int k = kt * 4 + q;
-                a[kt] = (fv && k < n) ? in[base + k * kstride] : 0.0;
+                a[kt] = (fv && kt * 4 + q < n) ? *p : 0.0;
+                p += 4 * kstride;
             }
         };
         long long t = seg + warp;
@@ -525,18 +536,19 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const 
             for (int it = 0; it < IT; ++it) c[it][0] = c[it][1] = 0.0;
 #pragma unroll
             for (int kt = 0; kt < KT; ++kt) {
-                if (kt < kt_n) {
+                if (kt < kt_n) {                // the one (warp-uniform) guard per k step
 #pragma unroll
-                    for (int it = 0; it < IT; ++it)
-                        if (it < it_n) dmma884(c[it][0], c[it][1], a[kt], brow[it * 8 * PITCH + kt * 4]);
+                    for (int it = 0; it < IT; ++it) dmma884(c[it][0], c[it][1], a[kt], brow[it * 8 * PITCH + kt * 4]);
                 }
             }
             if (fv) {
+                long long idx = base + 2 * q * kstride;
 #pragma unroll
                 for (int it = 0; it < IT; ++it) {
                     const int i = it * 8 + 2 * q;
-                    if (i < n) sink(base + i * kstride, c[it][0]);
-                    if (i + 1 < n) sink(base + (i + 1) * kstride, c[it][1]);
+                    if (i < n) sink(idx, c[it][0]);
+                    if (i + 1 < n) sink(idx + kstride, c[it][1]);
+                    idx += 8 * kstride;
                 }
             }
             if (PREFETCH) {
@@ -559,8 +571,25 @@ __device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const
     const int n = kv.shape[kv.modes[m].dim];
     if (n <= 8) kron_mode_fibre<8>(kv, m, in, smat, sink);
     else if (n < 12) kron_mode_fibre<16>(kv, m, in, smat, sink);
-    else if (n <= 32) kron_mode_dmma<32, PREFETCH>(kv, m, in, smat, sink);
-    else if (n <= KRON_NMAX_LIMIT) kron_mode_dmma<64, PREFETCH>(kv, m, in, smat, sink);
+    else if (n <= KRON_NMAX_LIMIT) {
+        const int it_n = (n + 7) >> 3;          // 2..8 output tiles
+        if constexpr (PREFETCH) {               // stand-alone kernels: exact tile count
+            switch (it_n) {
+            case 2: kron_mode_dmma<2, true>(kv, m, in, smat, sink); break;
+            case 3: kron_mode_dmma<3, true>(kv, m, in, smat, sink); break;
+            case 4: kron_mode_dmma<4, true>(kv, m, in, smat, sink); break;
+            case 5: kron_mode_dmma<5, true>(kv, m, in, smat, sink); break;
+            case 6: kron_mode_dmma<6, true>(kv, m, in, smat, sink); break;
+            case 7: kron_mode_dmma<7, true>(kv, m, in, smat, sink); break;
+            default: kron_mode_dmma<8, true>(kv, m, in, smat, sink); break;
+            }
+        } else {                                // loop kernels: even tile counts (zero-padded rows)
+            if (it_n <= 2) kron_mode_dmma<2, false>(kv, m, in, smat, sink);
+            else if (it_n <= 4) kron_mode_dmma<4, false>(kv, m, in, smat, sink);
+            else if (it_n <= 6) kron_mode_dmma<6, false>(kv, m, in, smat, sink);
+            else kron_mode_dmma<8, false>(kv, m, in, smat, sink);
+        }
+    }
     else kron_mode_pass(kv, m, in, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, sink);
 }
 #define KRON_SMAT_DOUBLES (KRON_NMAX_LIMIT * (KRON_NMAX_LIMIT + 4))
