@@ -534,9 +534,12 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const 
             double c[IT][2];
 #pragma unroll
             for (int it = 0; it < IT; ++it) c[it][0] = c[it][1] = 0.0;
+            // n > 8 (IT - 1) for the exact instantiations (PREFETCH) and n > 8 (IT - 2) for the even ones, so
+            // only the last 1 (3) k steps can be absent: the others form one straight-line block
+            constexpr int KT_SURE = PREFETCH ? KT - 1 : KT - 3;
 #pragma unroll
             for (int kt = 0; kt < KT; ++kt) {
-                if (kt < kt_n) {                // the one (warp-uniform) guard per k step
+                if (kt < KT_SURE || kt < kt_n) {
 #pragma unroll
                     for (int it = 0; it < IT; ++it) dmma884(c[it][0], c[it][1], a[kt], brow[it * 8 * PITCH + kt * 4]);
                 }
