@@ -162,8 +162,9 @@ def run_reference(args, shapes):
 
 def workload_config(shapes, gpus):
     N = int(np.prod(shapes))
+    tag = "BASELINE configs[1]" if tuple(shapes) == tuple(DEFAULT_SHAPES) else "non-default grid via --shapes"
     return {"workload": f"SSY {tuple(shapes)} grid, N={N}, dense fp64 P ({8 * N * N / 1e9:.1f} GB) resident in HBM, "
-                        f"w <- T w chained, w0=800 (BASELINE configs[1])",
+                        f"w <- T w chained, w0=800 ({tag})",
             "shapes": list(shapes), "N": N,
             "parallelism": f"row-shard x{gpus}" if gpus > 1 else "single GPU",
             "l2": "inputs larger than L2 (P >> 126 MB), no flush needed",
