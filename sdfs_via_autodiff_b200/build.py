@@ -9,7 +9,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsdfs_b200.so")
-SOURCES = ["api.cu", "builder.cu", "ops.cu", "loops.cu", "comm.cu", "sweep.cu", "small.cu"]
+SOURCES = ["api.cu", "builder.cu", "ops.cu", "loops.cu", "loops_dense.cu", "loops_kron_sa.cu", "loops_kron_newton.cu",
+           "loops_kron_anderson.cu", "loops_cont.cu",
+           "comm.cu", "sweep.cu", "small.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -36,18 +38,21 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     objs = []
     procs = []
-    for src in SOURCES:
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "sdfs_b200.h"))
+    hdr_time = max(os.path.getmtime(h) for h in headers)
+    for src in SOURCES:                       # one nvcc process per translation unit, all in parallel
         path = os.path.join(CSRC, src)
-        if not os.path.exists(path):
-            continue
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), hdr_time):
+            continue                          # object newer than its source and every header
         cmd = [nvcc, *NVCC_FLAGS, "-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
-        objs.append(obj)
     failed = False
     for src, p in procs:
         out = p.communicate()[0].decode()

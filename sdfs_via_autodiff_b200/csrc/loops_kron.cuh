@@ -1,0 +1,19 @@
+// Factor-form (Kronecker) instantiation of one loop kernel per translation unit: these are the
+// slowest units to compile (tensor-core contraction variants inlined at every apply site).
+#pragma once
+#include "loops.cuh"
+
+template <int WHICH>
+static int loop_launch_kron_t(sdfs_op *op, void *a, LoopEnv *env) {
+    sdfs_ctx *ctx = op->ctx;
+    const int64_t N = op->kv.N;
+    if (!op->kron_tmp[0]) {
+        CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[0], (size_t)N * sizeof(double)));
+        CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)N * sizeof(double)));
+    }
+    KronLoopOp lop{op->kv, op->kron_tmp[0], op->kron_tmp[1]};
+    return loop_launch<KronLoopOp, WHICH>(ctx, lop, a, env, lop.dyn_smem(), 2, (N + SDFS_THREADS - 1) / SDFS_THREADS, false);
+}
+int loop_launch_kron_sa(sdfs_op *op, void *a, LoopEnv *env);
+int loop_launch_kron_newton(sdfs_op *op, void *a, LoopEnv *env);
+int loop_launch_kron_anderson(sdfs_op *op, void *a, LoopEnv *env);

@@ -1,0 +1,3 @@
+#include "loops_kron.cuh"
+
+int loop_launch_kron_anderson(sdfs_op *op, void *a, LoopEnv *env) { return loop_launch_kron_t<LOOP_ANDERSON>(op, a, env); }

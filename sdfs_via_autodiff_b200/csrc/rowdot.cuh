@@ -596,3 +596,10 @@ __device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const
     else kron_mode_pass(kv, m, in, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, sink);
 }
 #define KRON_SMAT_DOUBLES (KRON_NMAX_LIMIT * (KRON_NMAX_LIMIT + 4))
+
+// Out-of-line storing contraction for the persistent loop kernels: they apply the operator at many
+// sites (T, JVP inside BiCGSTAB / GMRES, Anderson), and one shared copy of the non-final modes keeps
+// their code size (instruction-cache footprint, compile time) bounded.
+static __device__ __noinline__ void kron_mode_store(const KronView &kv, int m, const double *in, double *out, double *smat) {
+    kron_mode_apply(kv, m, in, smat, [&](int64_t idx, double s) { out[idx] = s; });
+}
