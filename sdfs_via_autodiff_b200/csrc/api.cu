@@ -60,6 +60,7 @@ int sdfs_ctx_create(int device, sdfs_ctx **out) {
     CUDA_TRY(nullptr, cudaMalloc(&ctx->d_status, 4096));
     CUDA_TRY(nullptr, cudaMemset(ctx->d_status, 0, 4096));
     CUDA_TRY(nullptr, cudaMallocHost(&ctx->h_status, 4096));
+    memset(ctx->h_status, 0, 4096);
     *out = ctx;
     return SDFS_OK;
 }
@@ -85,6 +86,8 @@ int sdfs_ctx_sync(sdfs_ctx *ctx) {
     ARG_CHECK(ctx, ctx != nullptr);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*(volatile long long *)ctx_h_abort(ctx))
+        return sdfs_set_error(ctx, SDFS_ERR_TIMEOUT, "a peer rank did not reach a fused exchange (30 s device-side timeout)");
     return SDFS_OK;
 }
 
@@ -121,6 +124,8 @@ int sdfs_timer_stop_ms(sdfs_ctx *ctx, double *ms) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+    if (*(volatile long long *)ctx_h_abort(ctx))
+        return sdfs_set_error(ctx, SDFS_ERR_TIMEOUT, "a peer rank did not reach a fused exchange (30 s device-side timeout)");
     float f = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
     *ms = (double)f;
@@ -195,6 +200,8 @@ int sdfs_d2h(sdfs_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*(volatile long long *)ctx_h_abort(ctx))
+        return sdfs_set_error(ctx, SDFS_ERR_TIMEOUT, "a peer rank did not reach a fused exchange (30 s device-side timeout)");
     return SDFS_OK;
 }
 

@@ -3,6 +3,7 @@
 // and a CUDA-IPC mapped exchange arena for the fused solver loops (peer stores
 // over NVLink + flag barrier, loops.cu).
 #include "common.cuh"
+#include "arena.cuh"
 #include <dlfcn.h>
 #include <stdlib.h>
 
@@ -114,7 +115,6 @@ int comm_allgather_rows(sdfs_ctx *ctx, double *d_vec, int64_t N) {
     return SDFS_OK;
 }
 
-size_t arena_bytes_for(int64_t maxN);                 // loops.cu
 
 extern "C" {
 

@@ -63,6 +63,8 @@ int sdfs_set_error(sdfs_ctx *ctx, int code, const char *fmt, ...);
                                   __FILE__, __LINE__, #cond);                           \
     } while (0)
 
+// pinned host word a kernel sets when a peer rank never reaches a fused exchange (checked at every sync)
+static inline long long *ctx_h_abort(sdfs_ctx *ctx) { return (long long *)((char *)ctx->h_status + 4096 - 64); }
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // ---------------------------------------------------------------------------

@@ -2,11 +2,6 @@
 // unit per operator type instantiates them).
 #include "loops.cuh"
 
-size_t arena_bytes_for(int64_t maxN) {
-    const size_t ldv = (size_t)round_up(maxN, 64) + 64;
-    return 1024 + arena_slots_doubles() * sizeof(double) + 2 * ldv * sizeof(double);
-}
-
 static int build_env(sdfs_op *op, LoopEnv *env) {
     sdfs_ctx *ctx = op->ctx;
     memset(env, 0, sizeof(*env));

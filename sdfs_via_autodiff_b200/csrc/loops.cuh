@@ -21,19 +21,13 @@
 #include "common.cuh"
 #include "rowdot.cuh"
 #include "cont.cuh"
+#include "arena.cuh"
 
-bool comm_peers_ready(sdfs_ctx *ctx);
-void *comm_peer_arena(sdfs_ctx *ctx, int r);
-int64_t comm_arena_maxN(sdfs_ctx *ctx);
-unsigned long long *comm_epoch(sdfs_ctx *ctx);
-int comm_allgather_rows(sdfs_ctx *ctx, double *d_vec, int64_t N);
 int small_sa_try(sdfs_op *op, const double *d_w_init, double tol, int64_t max_iter, double *d_w_out,
                  double *d_err_hist, int64_t hist_stride, int64_t hist_cap);   // small.cu
 
 #define TRY(x) do { int _rc = (x); if (_rc != SDFS_OK) return _rc; } while (0)
 
-#define NSETS 8            // reduction slot sets (one per phase, see phase tables below)
-#define NVAL 8             // values per set (GMRES orthogonalises against 8 basis vectors per barrier)
 #define HIST_CAP 120       // outer Newton iterations recorded in the status page
 #define GMRES_MAX_RESTART 64
 
@@ -59,28 +53,7 @@ struct LoopEnv {
     LoopStatus *status;
 };
 
-// ---- arena layout (shared with comm.cu) -----------------------------------
-static inline size_t arena_slots_doubles() { return (size_t)NSETS * SDFS_MAX_RANKS * SDFS_MAX_GRID * NVAL; }
-size_t arena_bytes_for(int64_t maxN);   // loops.cu
-static void arena_carve(void *base, int64_t maxN, unsigned long long **flags, double **slots, double **x0, double **x1) {
-    const size_t ldv = (size_t)round_up(maxN, 64) + 64;
-    char *b = (char *)base;
-    *flags = (unsigned long long *)b;
-    *slots = (double *)(b + 1024);
-    *x0 = *slots + arena_slots_doubles();
-    *x1 = *x0 + ldv;
-}
-
 // ---- device-side synchronisation and reductions ---------------------------
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // Barrier across every CTA of every rank.  Returns false (uniformly) after a peer
 // timeout so the kernel can unwind instead of hanging the GPU.
 __device__ __forceinline__ bool all_sync(cg::grid_group &grid, const LoopEnv &env, unsigned long long &epoch) {
@@ -99,7 +72,7 @@ __device__ __forceinline__ bool all_sync(cg::grid_group &grid, const LoopEnv &en
         st_release_sys(env.flags[peer] + env.rank, epoch);
         const long long t0 = clock64();
         while (ld_acquire_sys(env.flags[env.rank] + peer) < epoch) {
-            if (clock64() - t0 > 60000000000LL) {      // ~30 s: a peer died
+            if (clock64() - t0 > SDFS_PEER_TIMEOUT_CLOCKS) {
                 env.status->abort_code = 1;
                 break;
             }

@@ -1,13 +1,13 @@
 // Operator handles and single applications: T, JVP, SDF, plain P x.
 #include "common.cuh"
 #include "rowdot.cuh"
+#include "arena.cuh"
 #include "cont.cuh"
 
 int factors_to_kron(const sdfs_factors *f, KronView *kv);
 int launch_build_scalings(sdfs_ctx *ctx, const sdfs_factors *f, const KronView &kv, double gamma,
                           double theta, double mu_c, double *a_row, double *a_col, double *e_sdf);
 int launch_expand_dense(sdfs_ctx *ctx, const KronView &kv, int64_t row_begin, int64_t row_end, int64_t ld, double *P);
-int comm_allgather_rows(sdfs_ctx *ctx, double *d_vec, int64_t N);   // comm.cu
 
 #define TRY(x) do { int _rc = (x); if (_rc != SDFS_OK) return _rc; } while (0)
 
@@ -64,6 +64,55 @@ __device__ __forceinline__ void apply_epilogue(const EpiArgs &e, int64_t n, doub
     }
 }
 
+// single-output epilogues (T, JVP, plain P x) as a value, for the fused exchange below
+__device__ __forceinline__ double epilogue_value(const EpiArgs &e, int64_t n, double s0, double s1) {
+    if (e.mode == 0) return 1.0 + e.beta * pow(e.a_row[n] * s0, e.inv_theta);
+    if (e.mode == 1) {
+        const double ar = e.a_row[n];
+        return e.beta * pow(ar * s0, e.inv_theta - 1.0) * ar * s1;
+    }
+    return s0;
+}
+
+// Fused exchange of a row-sharded single application (one process per GPU): the epilogue stores its
+// rows straight into the result buffer of EVERY rank (NVLink peer stores into the CUDA-IPC arenas),
+// and the last CTA of the kernel to finish trades an epoch flag with the peers, so when the kernel
+// ends the full vector is in this rank's arena - no collective launch follows the row pass.
+struct PeerArgs {
+    int nranks, rank;                          // nranks <= 1: plain local stores through EpiArgs
+    double *out[SDFS_MAX_RANKS];               // result buffer y[epoch & 1] in rank r's arena
+    unsigned long long *sig[SDFS_MAX_RANKS];   // rank r's flag word for this rank
+    unsigned long long *mine;                  // this rank's flag words (written by the peers)
+    unsigned long long epoch;
+    unsigned int *counter;                     // CTAs of this launch that have finished (self-resetting)
+    long long *h_abort;                        // pinned host word: set when a peer never arrives
+};
+
+__device__ __forceinline__ void peer_exchange_finish(const PeerArgs &pa) {
+    __syncthreads();                           // every store of this CTA issued
+    if (threadIdx.x == 0) {
+        __threadfence_system();                // ... and ordered before the arrival count
+        const unsigned int done = atomicAdd(pa.counter, 1u);
+        if (done == gridDim.x - 1) {           // last CTA of this rank
+            *pa.counter = 0;
+            __threadfence_system();
+            for (int r = 0; r < pa.nranks; ++r)
+                if (r != pa.rank) st_release_sys(pa.sig[r], pa.epoch);
+            const long long t0 = clock64();
+            for (int r = 0; r < pa.nranks; ++r) {
+                if (r == pa.rank) continue;
+                while (ld_acquire_sys(pa.mine + r) < pa.epoch) {
+                    if (clock64() - t0 > SDFS_PEER_TIMEOUT_CLOCKS) {
+                        *(volatile long long *)pa.h_abort = 1;
+                        __threadfence_system();
+                        return;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // elementwise epilogue at full occupancy (factor-form path: the contraction kernels run at 8-12
 // warps per SM, far too few to hide the latency of one pow per output)
 __global__ void k_epilogue_ew(int64_t N, const double *__restrict__ s0, const double *__restrict__ s1, EpiArgs e) {
@@ -73,12 +122,21 @@ __global__ void k_epilogue_ew(int64_t N, const double *__restrict__ s0, const do
 
 template <int NX>
 __global__ void __launch_bounds__(SDFS_THREADS, 1)
-k_dense_apply(const __grid_constant__ DenseView dv, const double *x0, const double *x1, EpiArgs e) {
+k_dense_apply(const __grid_constant__ DenseView dv, const double *x0, const double *x1, EpiArgs e,
+              const __grid_constant__ PeerArgs pa) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     RowPipe<NX> *rp = reinterpret_cast<RowPipe<NX> *>(dyn_smem);
     PipeState st;
     if (dv.vec2) pipe_init(rp, st);
-    dense_pass<NX>(dv, x0, x1, rp, st, [&](int64_t n, double s0, double s1) { apply_epilogue<false>(e, n, s0, s1); });
+    if (pa.nranks > 1) {
+        dense_pass<NX>(dv, x0, x1, rp, st, [&](int64_t n, double s0, double s1) {
+            const double val = epilogue_value(e, n, s0, s1);
+            for (int r = 0; r < pa.nranks; ++r) pa.out[r][n] = val;
+        });
+        peer_exchange_finish(pa);
+    } else {
+        dense_pass<NX>(dv, x0, x1, rp, st, [&](int64_t n, double s0, double s1) { apply_epilogue<false>(e, n, s0, s1); });
+    }
 }
 
 __global__ void __launch_bounds__(256) k_kron_mode(KronView kv, int m, const double *__restrict__ in, double *__restrict__ out) {
@@ -146,13 +204,14 @@ static inline int dense_grid(sdfs_ctx *ctx, const DenseView &dv) {
 }
 
 template <int NX>
-static int launch_dense_apply(sdfs_ctx *ctx, const DenseView &dv, const double *x0, const double *x1, const EpiArgs &e) {
+static int launch_dense_apply(sdfs_ctx *ctx, const DenseView &dv, const double *x0, const double *x1, const EpiArgs &e,
+                              const PeerArgs &pa) {
     const size_t smem = dv.vec2 ? sizeof(RowPipe<NX>) : 0;
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_dense_apply<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(RowPipe<NX>)));
     const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
     if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
-    k_dense_apply<NX><<<dense_grid(ctx, dv), SDFS_THREADS, smem, ctx->stream>>>(dv, x0, x1, e);
+    k_dense_apply<NX><<<dense_grid(ctx, dv), SDFS_THREADS, smem, ctx->stream>>>(dv, x0, x1, e, pa);
     if (prof) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
         ctx->prof_used += 2;
@@ -240,12 +299,36 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
     else k_prologue<true><<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(pmode, N, a_col, d_w, d_v, theta, x0, x1);
     ctx->launches++;
     if (dense) {
-        if (op->dv.row_end > op->dv.row_begin) {
-            if (nx == 1) TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e));
-            else TRY(launch_dense_apply<2>(ctx, op->dv, x0, x1, e));
+        const bool sharded = ctx->nranks > 1 && op->dv.row_end - op->dv.row_begin < N;
+        PeerArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        // fused exchange: single-output applies of a sharded operator once the arenas are mapped
+        // (SDFS_FUSED_EXCHANGE=0 forces the NCCL all-gather path: used by the A/B measurement)
+        static const bool fused_allowed = !(getenv("SDFS_FUSED_EXCHANGE") && atoi(getenv("SDFS_FUSED_EXCHANGE")) == 0);
+        const bool fused = sharded && fused_allowed && e.mode != 2 && gather0 && e.out0 && comm_peers_ready(ctx) &&
+                           comm_arena_maxN(ctx) >= N;
+        if (fused) {
+            unsigned long long *ep = comm_epoch(ctx);
+            *ep += 1;                                           // every rank issues the same sequence
+            pa.nranks = ctx->nranks; pa.rank = ctx->rank; pa.epoch = *ep;
+            for (int r = 0; r < ctx->nranks; ++r) {
+                void *base = comm_peer_arena(ctx, r);
+                pa.out[r] = arena_apply_buf(base, comm_arena_maxN(ctx), (int)(*ep & 1));
+                pa.sig[r] = (unsigned long long *)base + ctx->rank;
+            }
+            pa.mine = (unsigned long long *)comm_peer_arena(ctx, ctx->rank);
+            pa.counter = (unsigned int *)((char *)ctx->d_status + 4096 - 64);
+            pa.h_abort = ctx_h_abort(ctx);
+        }
+        // a rank without rows still takes part in the exchange (one CTA, empty pass)
+        if (op->dv.row_end > op->dv.row_begin || fused) {
+            if (nx == 1) TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e, pa));
+            else TRY(launch_dense_apply<2>(ctx, op->dv, x0, x1, e, pa));
         }
         CUDA_TRY(ctx, cudaGetLastError());
-        if (ctx->nranks > 1 && op->dv.row_end - op->dv.row_begin < N) {
+        if (fused) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(e.out0, pa.out[ctx->rank], (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        } else if (sharded) {
             if (gather0 && e.out0) TRY(comm_allgather_rows(ctx, e.out0, N));
             if (gather1 && e.out1) TRY(comm_allgather_rows(ctx, e.out1, N));
         }
@@ -532,9 +615,11 @@ int sdfs_op_bench_pass(sdfs_op *op, int mode, int reps, double *avg_ms) {
     double *x0 = op->work, *scratch = op->work + 3 * op->ldv;
     EpiArgs e{mode, op->dv.a_row, nullptr, nullptr, op->dv.beta, op->dv.theta, scratch, nullptr};
     e.inv_theta = 1.0 / e.theta;
-    TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e));
+    PeerArgs pa;
+    memset(&pa, 0, sizeof(pa));                 // local pass only
+    TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e, pa));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int i = 0; i < reps; ++i) TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e));
+    for (int i = 0; i < reps; ++i) TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e, pa));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
     float ms = 0.f;

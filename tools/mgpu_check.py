@@ -35,7 +35,16 @@ for shapes in ((2, 3, 4, 5), (7, 5, 6, 9), (10, 10, 10, 10)):
     rng = np.random.default_rng(1233)
     w = np.exp(rng.standard_normal(shapes))
     got = np.asarray(op(w))
-    report(f"{shapes} T (NCCL all-gather)", np.allclose(got, kop.T(w), rtol=1e-12, atol=0))
+    path = "NCCL all-gather" if os.environ.get("SDFS_FUSED_EXCHANGE") == "0" else "fused peer-store exchange"
+    report(f"{shapes} T ({path})", np.allclose(got, kop.T(w), rtol=1e-12, atol=0))
+    # chained applications without host round trips: exercises the double-buffered result slots
+    wd = ctx.asarray(w) if hasattr(ctx, "asarray") else op._in(w)
+    ref = w
+    for _ in range(7):
+        wd = op(wd)
+        ref = kop.T(ref)
+    report(f"{shapes} 7 chained T ({path})", np.allclose(np.asarray(wd), ref, rtol=1e-11, atol=0))
+    report(f"{shapes} P 1 = 1 ({path})", np.allclose(np.asarray(op.apply_P(np.ones(shapes))), 1.0, rtol=0, atol=1e-12))
     v = rng.standard_normal(shapes)
     report(f"{shapes} JVP", np.allclose(np.asarray(op.jvp(w, v)), kop.jvp(w, v), rtol=1e-10, atol=1e-12))
     t0 = time.time()
