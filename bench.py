@@ -28,6 +28,9 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: NCCL's banner / debug output (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
