@@ -191,7 +191,9 @@ int op_ensure_work(sdfs_op *op, int n_vectors) {
 
 static inline int ew_grid(sdfs_ctx *ctx, int64_t N) {
     int64_t g = (N + 255) / 256;
-    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    // several waves of CTAs: a grid of exactly 8 per SM leaves a quarter-occupancy tail wave when the
+    // kernel's registers admit only 6 resident CTAs (k_epilogue_ew at 9.8 M states: 96 -> 7x us)
+    const int64_t cap = (int64_t)ctx->sm_count * 32;
     return (int)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 

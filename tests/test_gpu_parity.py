@@ -655,3 +655,23 @@ def test_factor_form_ragged_axes_tensor_core_modes(model, shapes):
     wn, _ = S.newton_solver(op, np.full(shapes, 800.0), tol=1e-9, bicgstab_atol=1e-10, verbose=False)
     wn = np.asarray(wn)
     assert np.max(np.abs(kop.T(wn) - wn)) < 1e-6 * np.max(wn)
+
+
+def test_factor_form_large_axes_every_tile_count_vs_oracle():
+    """6.9 M states with axes 40 / 48 / 56 / 64: the stand-alone tensor-core contraction at 5, 6, 7
+    and 8 output tiles (exact instantiations) and the loop kernels' even-count variants, against the
+    oracle's einsum form; P 1 = 1 as the size-independent property."""
+    shapes = (40, 48, 56, 64)
+    mdl = O.SSY()
+    arrays = O.discretize_ssy(mdl, shapes)
+    kop = O.KronSSY(shapes, mdl.params, arrays)
+    op = S.make_T_ssy(mdl, shapes, arrays, storage="kron")
+    np.testing.assert_allclose(np.asarray(op.apply_P(np.ones(shapes))), 1.0, rtol=0, atol=1e-12)
+    rng = np.random.default_rng(1233)
+    w = 500 + 400 * rng.random(shapes)
+    v = rng.standard_normal(shapes)
+    np.testing.assert_allclose(np.asarray(op(w)), kop.T(w), rtol=RTOL_T)
+    np.testing.assert_allclose(np.asarray(op.jvp(w, v)), kop.jvp(w, v), rtol=1e-10, atol=1e-11)
+    ws, k = S.successive_approx(op, w, tol=0.0, max_iter=3, verbose=False)      # loop-kernel variants
+    ref = kop.T(kop.T(kop.T(w)))
+    np.testing.assert_allclose(np.asarray(ws), ref, rtol=1e-11)
