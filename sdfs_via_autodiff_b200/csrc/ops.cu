@@ -22,7 +22,18 @@ template <bool FAST>   // FAST: exp(e log x) power form (factor-form path, where
 __global__ void k_prologue(int mode, int64_t N, const double *__restrict__ a_col, const double *__restrict__ w,
                            const double *__restrict__ v, double theta, double *__restrict__ x0,
                            double *__restrict__ x1) {
-    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (FAST && mode == 0) {        // two independent log/exp chains per thread (the T prologue at 10^7 states)
+        for (; n + stride < N; n += 2 * stride) {
+            const double wa = w[n], wb = w[n + stride];
+            const double aa = a_col[n], ab = a_col[n + stride];
+            const double ta = pow_pos(wa, theta), tb = pow_pos(wb, theta);
+            x0[n] = aa * ta;
+            x0[n + stride] = ab * tb;
+        }
+    }
+    for (; n < N; n += stride) {
         if (mode == 3) { x0[n] = v[n]; continue; }
         const double wn = w[n];
         const double wt = FAST ? pow_pos(wn, theta) : pow(wn, theta);
@@ -116,8 +127,17 @@ __device__ __forceinline__ void peer_exchange_finish(const PeerArgs &pa) {
 // elementwise epilogue at full occupancy (factor-form path: the contraction kernels run at 8-12
 // warps per SM, far too few to hide the latency of one pow per output)
 __global__ void k_epilogue_ew(int64_t N, const double *__restrict__ s0, const double *__restrict__ s1, EpiArgs e) {
-    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x)
-        apply_epilogue<true>(e, n, s0[n], s1 ? s1[n] : s0[n]);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e.mode == 0) {              // T: two independent log/exp chains per thread
+        for (; n + stride < N; n += 2 * stride) {
+            const double xa = e.a_row[n] * s0[n], xb = e.a_row[n + stride] * s0[n + stride];
+            const double pa = pow_pos(xa, e.inv_theta), pb = pow_pos(xb, e.inv_theta);
+            e.out0[n] = 1.0 + e.beta * pa;
+            e.out0[n + stride] = 1.0 + e.beta * pb;
+        }
+    }
+    for (; n < N; n += stride) apply_epilogue<true>(e, n, s0[n], s1 ? s1[n] : s0[n]);
 }
 
 template <int NX>
