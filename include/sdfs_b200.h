@@ -220,6 +220,14 @@ int sdfs_sweep_solve_newton(sdfs_op *op, const double *h_prefs, int64_t B, doubl
 /* one batched T step on a resident panel (bench / tests): d_W_in, d_W_out N x B */
 int sdfs_sweep_apply_T(sdfs_op *op, const double *h_prefs, int64_t B,
                        const double *d_W_in, double *d_W_out);
+/* How the sweep forms S = P V for all columns:
+ *   SDFS_SWEEP_DENSE  (0, default) the fp64 tensor-core GEMM against the stored P (BASELINE config 5);
+ *   SDFS_SWEEP_FACTOR (1) the sum-factorised contraction over the Markov factors, batched over the
+ *                     columns (16 N B bytes per mode instead of 2 N^2 B flop): same results to
+ *                     rounding, same per-column iteration counts. */
+#define SDFS_SWEEP_DENSE  0
+#define SDFS_SWEEP_FACTOR 1
+int sdfs_sweep_set_form(sdfs_op *op, int form);
 
 /* ---- multi-GPU (one process per GPU) -------------------------------------
  * Row-sharded dense operators: rank g owns rows [N g/G, N (g+1)/G) of P and the

@@ -85,6 +85,7 @@ _SIGS = {
     "sdfs_sweep_solve_newton": (C.c_int, [c_vp, P(c_f64), c_i64, c_f64, c_f64, c_i64, c_f64, c_f64, c_i64, c_vp,
                                           P(c_i64), P(c_f64), P(c_i64), P(c_i64)]),
     "sdfs_sweep_apply_T": (C.c_int, [c_vp, P(c_f64), c_i64, c_vp, c_vp]),
+    "sdfs_sweep_set_form": (C.c_int, [c_vp, C.c_int]),
     "sdfs_comm_unique_id": (C.c_int, [c_vp]),
     "sdfs_comm_init": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
     "sdfs_comm_rank": (C.c_int, [c_vp, P(C.c_int), P(C.c_int)]),

@@ -150,6 +150,7 @@ struct sdfs_op {
     double *slots = nullptr;           // reduction slots (single-GPU arena)
     double *kron_tmp[2] = {nullptr, nullptr};
     double gamma = 0, psi = 0, mu_c = 0;  // remembered for set_preferences
+    int sweep_form = 0;                // SDFS_SWEEP_DENSE | SDFS_SWEEP_FACTOR
 };
 
 int op_ensure_work(sdfs_op *op, int n_vectors);

@@ -304,6 +304,26 @@ static int run_cont(sdfs_op *op, int which, const double *d_w, const double *d_v
     return SDFS_OK;
 }
 
+// One mode contraction out = (I x .. x M_m x .. x I) in of a factor-form view (also used by the
+// batched sweep, sweep.cu, on a view with a leading column axis).
+int launch_kron_mode(sdfs_ctx *ctx, const KronView &kv, int m, const double *in, double *out) {
+    static const int kron_tc_threads = getenv("SDFS_KRON_THREADS") ? atoi(getenv("SDFS_KRON_THREADS")) : 256;
+    static const int kron_tc_ctas = getenv("SDFS_KRON_CTAS") ? atoi(getenv("SDFS_KRON_CTAS")) : 2;
+    const KronMode &md = kv.modes[m];
+    // tensor-core contraction (n >= 12): 8 warps per CTA, each on tiles of 8 fibres, one contiguous
+    // tile range per CTA; register-tiled FMA contraction (short axes): one fibre per thread,
+    // work items dealt round-robin (any grid size is valid)
+    const int nm = kv.shape[md.dim];
+    const long long fibres = md.Fcount * md.Mcount;
+    const bool tc = nm >= 12 && nm <= KRON_NMAX_LIMIT;
+    const int threads = tc ? kron_tc_threads : (fibres >= (long long)ctx->sm_count * 128 ? 128 : 64);
+    const int grid = tc ? ctx->sm_count * kron_tc_ctas : ctx->sm_count * 6;
+    k_kron_mode<<<grid, threads, 0, ctx->stream>>>(kv, m, in, out);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SDFS_OK;
+}
+
 // Shared driver: prologue -> P pass(es) -> epilogue.
 static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_v, EpiArgs e, bool gather0,
                      bool gather1) {
@@ -361,24 +381,13 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)N * sizeof(double)));
         }
         // work items of the fibre kernel are distributed round-robin: any grid size is valid
-        static const int kron_tc_threads = getenv("SDFS_KRON_THREADS") ? atoi(getenv("SDFS_KRON_THREADS")) : 256;
-        static const int kron_tc_ctas = getenv("SDFS_KRON_CTAS") ? atoi(getenv("SDFS_KRON_CTAS")) : 2;
         double *sfin[2] = {op->work + 2 * op->ldv, op->work + 3 * op->ldv};     // finished contractions
         for (int pass = 0; pass < nx; ++pass) {
             const double *in = (pass == 0) ? x0 : x1;
             for (int m = 0; m < kv.n_modes; ++m) {
-                const bool last_mode = (m == kv.n_modes - 1);
-                // tensor-core contraction (n >= 12): 8 warps per CTA, each on tiles of 8 fibres;
-                // register-tiled FMA contraction (short axes): one fibre per thread
-                const int nm = kv.shape[kv.modes[m].dim];
-                const int64_t fibres = N / nm;
-                const bool tc = nm >= 12 && nm <= KRON_NMAX_LIMIT;
-                const int threads = tc ? kron_tc_threads : (fibres >= (int64_t)ctx->sm_count * 128 ? 128 : 64);
-                const int grid = tc ? ctx->sm_count * kron_tc_ctas : ctx->sm_count * 6;
-                double *out = last_mode ? sfin[pass] : op->kron_tmp[m & 1];
-                k_kron_mode<<<grid, threads, 0, ctx->stream>>>(kv, m, in, out);
+                double *out = (m == kv.n_modes - 1) ? sfin[pass] : op->kron_tmp[m & 1];
+                TRY(launch_kron_mode(ctx, kv, m, in, out));
                 in = out;
-                ctx->launches++;
             }
         }
         k_epilogue_ew<<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(N, sfin[0], nx > 1 ? sfin[1] : nullptr, e);

@@ -222,11 +222,14 @@ struct SweepWork {
     long long *iters = nullptr;
     int *done = nullptr, *n_active = nullptr;
     double *V = nullptr, *Wa = nullptr, *Wb = nullptr;      // panels [B][ldw]
+    double *T0 = nullptr, *T1 = nullptr;                    // factor form: mode ping-pong panels
+    bool factor_form = false;
+    KronView kb{};                                          // factor view with a leading column axis
     int64_t ldw = 0;
     void free_all() {
-        void *ps[] = {hl, sc, mz, gamma, theta, beta, last_err, err_bits, iters, done, n_active, V, Wa, Wb};
+        void *ps[] = {hl, sc, mz, gamma, theta, beta, last_err, err_bits, iters, done, n_active, V, Wa, Wb, T0, T1};
         for (void *p : ps) if (p) cudaFree(p);
-        hl = sc = mz = gamma = theta = beta = last_err = V = Wa = Wb = nullptr;
+        hl = sc = mz = gamma = theta = beta = last_err = V = Wa = Wb = T0 = T1 = nullptr;
         err_bits = nullptr; iters = nullptr; done = n_active = nullptr;
     }
     ~SweepWork() { free_all(); }     // error paths return early: nothing may leak
@@ -234,11 +237,12 @@ struct SweepWork {
 
 static int sweep_setup(sdfs_op *op, const double *h_prefs, int64_t B, bool panels, SweepWork *w) {
     sdfs_ctx *ctx = op->ctx;
-    if (op->storage != SDFS_STORAGE_DENSE || !op->factors)
-        return sdfs_set_error(ctx, SDFS_ERR_ARG, "sweep needs a dense operator built from factors");
-    if (op->dv.row_begin != 0 || op->dv.row_end != op->dv.N)
+    if (!op->factors || (op->storage != SDFS_STORAGE_DENSE && op->storage != SDFS_STORAGE_KRON))
+        return sdfs_set_error(ctx, SDFS_ERR_ARG, "sweep needs an operator built from factors");
+    w->factor_form = op->storage == SDFS_STORAGE_KRON || op->sweep_form == SDFS_SWEEP_FACTOR;
+    if (!w->factor_form && (op->dv.row_begin != 0 || op->dv.row_end != op->dv.N))
         return sdfs_set_error(ctx, SDFS_ERR_ARG, "sweep needs the full P on this rank (columns, not rows, are sharded)");
-    const int64_t N = op->dv.N;
+    const int64_t N = op->kv.N;
     w->ldw = round_up(N, 64);
     const sdfs_factors *f = op->factors;
     CUDA_TRY(ctx, cudaMalloc(&w->hl, N * 8)); CUDA_TRY(ctx, cudaMalloc(&w->sc, N * 8)); CUDA_TRY(ctx, cudaMalloc(&w->mz, N * 8));
@@ -269,6 +273,21 @@ static int sweep_setup(sdfs_op *op, const double *h_prefs, int64_t B, bool panel
     const size_t pbytes = (size_t)B * w->ldw * 8;
     CUDA_TRY(ctx, cudaMalloc(&w->V, pbytes));
     CUDA_TRY(ctx, cudaMemsetAsync(w->V, 0, pbytes, ctx->stream));
+    if (w->factor_form) {
+        CUDA_TRY(ctx, cudaMalloc(&w->T0, pbytes)); CUDA_TRY(ctx, cudaMalloc(&w->T1, pbytes));
+        // every mode gains the column index as its outermost free axis (stride ldw): all B columns
+        // go through one launch per mode
+        w->kb = op->kv;
+        for (int m = 0; m < w->kb.n_modes; ++m) {
+            KronMode &md = w->kb.modes[m];
+            if (md.nF + md.nM >= SDFS_MAX_DIMS)
+                return sdfs_set_error(ctx, SDFS_ERR_UNSUPPORTED, "factor-form sweep: too many axes");
+            for (int a = md.nF; a > 0; --a) { md.Fshape[a] = md.Fshape[a - 1]; md.Fstride[a] = md.Fstride[a - 1]; }
+            md.Fshape[0] = (int)B; md.Fstride[0] = w->ldw;
+            md.nF += 1;
+            md.Fcount *= B;
+        }
+    }
     if (panels) {
         CUDA_TRY(ctx, cudaMalloc(&w->Wa, pbytes)); CUDA_TRY(ctx, cudaMalloc(&w->Wb, pbytes));
         CUDA_TRY(ctx, cudaMemsetAsync(w->Wa, 0, pbytes, ctx->stream));
@@ -280,7 +299,7 @@ static int sweep_setup(sdfs_op *op, const double *h_prefs, int64_t B, bool panel
 
 static int sweep_gemm(sdfs_op *op, SweepWork &w, int64_t B, const double *V, const SweepEpi &ep, const SweepCols &sc) {
     sdfs_ctx *ctx = op->ctx;
-    const int64_t N = op->dv.N;
+    const int64_t N = op->kv.N;
     const int tiles_m = (int)((N + GM - 1) / GM);
     // column-tile width: 128 unless 64 fills the last wave of CTAs markedly better (one CTA per SM;
     // a 64-wide tile does half the work of a 128-wide one at ~90 % of its per-tile efficiency)
@@ -309,6 +328,87 @@ static int sweep_gemm(sdfs_op *op, SweepWork &w, int64_t B, const double *V, con
     return SDFS_OK;
 }
 
+// Factor form: the GEMM epilogue as an elementwise kernel.  One CTA per (column, chunk of rows), so the
+// per-column scalars are uniform in the CTA and the sup-norm needs one atomic per CTA.
+#define SWE_ROWS 2048
+__global__ void __launch_bounds__(256) k_sweep_epi_ew(int64_t N, int64_t ldw, const double *__restrict__ S,
+                                                       const double *__restrict__ sig_c, const double *__restrict__ mz,
+                                                       SweepEpi ep, SweepCols sc) {
+    const int64_t chunks = (N + SWE_ROWS - 1) / SWE_ROWS;
+    const int64_t b = blockIdx.x / chunks, n0 = (blockIdx.x % chunks) * SWE_ROWS;
+    const int64_t n1 = n0 + SWE_ROWS < N ? n0 + SWE_ROWS : N;
+    const double *Sb = S + b * ldw;
+    if (ep.mode == 2) {
+        for (int64_t n = n0 + threadIdx.x; n < n1; n += blockDim.x)
+            ep.out0[b * ldw + n] = ep.D[b * ldw + n] * Sb[n] - ep.Vsub[b * ldw + n];
+        return;
+    }
+    const double g = sc.gamma[b], th = sc.theta[b], be = sc.beta[b];
+    const int frozen = sc.done ? sc.done[b] : 0;
+    const double omg = 1.0 - g, inv_th = 1.0 / th;
+    double emax = 0.0;
+    for (int64_t n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
+        const double t2 = omg * sig_c[n];
+        const double a_row = exp(0.5 * (t2 * t2)) * exp(omg * mz[n]);
+        const double w_old = ep.W[b * ldw + n];
+        const double sv = a_row * Sb[n];
+        double y = 1.0 + be * pow(sv, inv_th);
+        if (ep.mode == 0) {
+            if (frozen) y = w_old;
+            ep.out0[b * ldw + n] = y;
+            const double d = fabs(y - w_old);
+            emax = (d != d || emax != emax) ? d + emax : fmax(emax, d);   // NaN propagates
+        } else {
+            ep.out0[b * ldw + n] = y - w_old;
+            ep.out1[b * ldw + n] = be * pow(sv, (1.0 - th) * inv_th) * a_row;
+        }
+    }
+    if (ep.mode == 0 && ep.err_bits) {
+        __shared__ double red[8];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, emax, o);
+            emax = (other != other || emax != emax) ? other + emax : fmax(emax, other);
+        }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = emax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double e = red[0];
+            for (int i = 1; i < (int)(blockDim.x >> 5); ++i) e = (red[i] != red[i] || e != e) ? red[i] + e : fmax(e, red[i]);
+            atomicMax(ep.err_bits + b, (unsigned long long)__double_as_longlong(fabs(e)));
+        }
+    }
+}
+
+int launch_kron_mode(sdfs_ctx *ctx, const KronView &kv, int m, const double *in, double *out);   // ops.cu
+
+// S = P V for all columns through the Markov factors (one launch per mode, columns batched), then the epilogue
+static int sweep_factor(sdfs_op *op, SweepWork &w, int64_t B, const double *V, const SweepEpi &ep, const SweepCols &sc) {
+    sdfs_ctx *ctx = op->ctx;
+    const int64_t N = op->kv.N;
+    const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
+    if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
+    const double *in = V;
+    for (int m = 0; m < w.kb.n_modes; ++m) {
+        double *out = (m & 1) ? w.T1 : w.T0;
+        TRY(launch_kron_mode(ctx, w.kb, m, in, out));
+        in = out;
+    }
+    const int64_t chunks = (N + SWE_ROWS - 1) / SWE_ROWS;
+    k_sweep_epi_ew<<<(unsigned)(B * chunks), 256, 0, ctx->stream>>>(N, w.ldw, in, w.sc, w.mz, ep, sc);
+    if (prof) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
+        ctx->prof_used += 2;
+    }
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SDFS_OK;
+}
+
+static inline int sweep_PV(sdfs_op *op, SweepWork &w, int64_t B, const double *V, const SweepEpi &ep, const SweepCols &sc) {
+    return w.factor_form ? sweep_factor(op, w, B, V, ep, sc) : sweep_gemm(op, w, B, V, ep, sc);
+}
+
 static inline int panel_grid(sdfs_ctx *ctx, int64_t tot) {
     const int64_t g = (tot + 255) / 256, cap = (int64_t)ctx->sm_count * 16;
     return (int)(g < cap ? (g > 0 ? g : 1) : cap);
@@ -316,12 +416,12 @@ static inline int panel_grid(sdfs_ctx *ctx, int64_t tot) {
 
 static int sweep_step(sdfs_op *op, SweepWork &w, int64_t B, const double *Win, double *Wout, bool track) {
     sdfs_ctx *ctx = op->ctx;
-    const int64_t N = op->dv.N;
+    const int64_t N = op->kv.N;
     SweepCols sc{w.gamma, w.theta, w.beta, track ? w.done : nullptr};
     k_sweep_prologue<<<panel_grid(ctx, N * B), 256, 0, ctx->stream>>>(N, B, w.ldw, w.hl, Win, sc, w.V);
     ctx->launches++;
     SweepEpi ep{0, Win, Wout, nullptr, nullptr, nullptr, track ? w.err_bits : nullptr};
-    return sweep_gemm(op, w, B, w.V, ep, sc);
+    return sweep_PV(op, w, B, w.V, ep, sc);
 }
 
 
@@ -338,6 +438,15 @@ __global__ void k_copy_panel(const double *src, int64_t lds, double *dst, int64_
 
 extern "C" {
 
+int sdfs_sweep_set_form(sdfs_op *op, int form) {
+    if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_sweep_set_form: NULL op");
+    ARG_CHECK(op->ctx, form == SDFS_SWEEP_DENSE || form == SDFS_SWEEP_FACTOR);
+    if (form == SDFS_SWEEP_DENSE && op->storage != SDFS_STORAGE_DENSE)
+        return sdfs_set_error(op->ctx, SDFS_ERR_ARG, "the dense (GEMM) sweep needs a dense operator");
+    op->sweep_form = form;
+    return SDFS_OK;
+}
+
 int sdfs_sweep_apply_T(sdfs_op *op, const double *h_prefs, int64_t B, const double *d_W_in, double *d_W_out) {
     if (!op) return sdfs_set_error(nullptr, SDFS_ERR_ARG, "sdfs_sweep_apply_T: NULL op");
     sdfs_ctx *ctx = op->ctx;
@@ -345,7 +454,7 @@ int sdfs_sweep_apply_T(sdfs_op *op, const double *h_prefs, int64_t B, const doub
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     SweepWork w;
     int rc = sweep_setup(op, h_prefs, B, true, &w);
-    const int64_t N = op->dv.N;
+    const int64_t N = op->kv.N;
     const int grid = ctx->sm_count * 8;
     if (rc == SDFS_OK) {
         k_copy_panel<<<grid, 256, 0, ctx->stream>>>(d_W_in, N, w.Wa, w.ldw, N, B);
@@ -369,7 +478,7 @@ int sdfs_sweep_solve_sa(sdfs_op *op, const double *h_prefs, int64_t B, double w_
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     SweepWork w;
     int rc = sweep_setup(op, h_prefs, B, true, &w);
-    const int64_t N = op->dv.N;
+    const int64_t N = op->kv.N;
     const int grid = ctx->sm_count * 8;
     double *cur = w.Wa, *nxt = w.Wb;
     if (rc == SDFS_OK) {
@@ -608,7 +717,7 @@ extern "C" int sdfs_sweep_solve_newton(sdfs_op *op, const double *h_prefs, int64
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     SweepWork w;
     int rc = sweep_setup(op, h_prefs, B, false, &w);
-    const int64_t N = op->dv.N;
+    const int64_t N = op->kv.N;
     const long long kmax = krylov_maxiter > 0 ? krylov_maxiter : 10 * N;
     double *pan = nullptr, *sca = nullptr;
     long long *lls = nullptr;
@@ -653,7 +762,7 @@ extern "C" int sdfs_sweep_solve_newton(sdfs_op *op, const double *h_prefs, int64
         while (rc == SDFS_OK && n_out > 0) {
             k_swn_prologue<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, w.hl, sc, st, p);
             SweepEpi e1{1, p.W, p.G, p.D, nullptr, nullptr, nullptr};
-            rc = sweep_gemm(op, w, B, p.Xin, e1, sc);
+            rc = sweep_PV(op, w, B, p.Xin, e1, sc);
             ++gemms;
             if (rc) break;
             cudaMemsetAsync(st.n_in_active, 0, 4, ctx->stream);
@@ -664,11 +773,11 @@ extern "C" int sdfs_sweep_solve_newton(sdfs_op *op, const double *h_prefs, int64
             while (rc == SDFS_OK && n_in > 0) {
                 k_swn_phase1<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, st, p);
                 SweepEpi e2{2, nullptr, p.Q, nullptr, p.D, p.Pv, nullptr};
-                rc = sweep_gemm(op, w, B, p.Xin, e2, sc);
+                rc = sweep_PV(op, w, B, p.Xin, e2, sc);
                 if (rc) break;
                 k_swn_phase3<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, st, p);
                 SweepEpi e3{2, nullptr, p.T, nullptr, p.D, p.Sv, nullptr};
-                rc = sweep_gemm(op, w, B, p.Xin, e3, sc);
+                rc = sweep_PV(op, w, B, p.Xin, e3, sc);
                 if (rc) break;
                 k_swn_phase5<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, kmax, st, p);
                 ctx->launches += 3;

@@ -1,9 +1,12 @@
 """Batched (γ, ψ, β) parameter sweeps (BASELINE config 5).
 
 All parameter sets share one transition matrix P (P depends only on the ρ's and s's),
-so one T step for B parameter sets is the fp64 tensor-core GEMM S = P·V with per-column
-prologue/epilogue (csrc/sweep.cu).  Across GPUs the columns are sharded (P replicated);
-no collective is needed until the results are gathered.
+so one T step for B parameter sets is S = P·V with per-column prologue/epilogue
+(csrc/sweep.cu): either the fp64 tensor-core GEMM against the stored P (``form="dense"``, the
+form BASELINE config 5 names) or the sum-factorised contraction over the Markov factors batched
+over the columns (``form="factor"``: 16·N·B bytes per mode instead of 2·N²·B flop, no P in
+memory).  Across GPUs the columns are sharded; no collective is needed until the results are
+gathered.
 """
 import ctypes as C
 
@@ -11,19 +14,29 @@ import numpy as np
 
 from ._lib import lib, check
 from .device import Context
-from .operator import Factors, WCOperator, MODEL_SSY, MODEL_GCY, STORAGE_DENSE
+from .operator import Factors, WCOperator, MODEL_SSY, MODEL_GCY, STORAGE_DENSE, STORAGE_KRON
 
 STORAGE_DENSE_REPLICATED = 2
+SWEEP_DENSE, SWEEP_FACTOR = 0, 1
 
 
-def make_sweep_operator(model, shapes, ctx=None):
-    """Dense operator holding the full P on this rank (columns, not rows, are sharded)."""
+def make_sweep_operator(model, shapes, ctx=None, form="dense"):
+    """Operator for batched sweeps on this rank (columns, not rows, are sharded).
+
+    ``form="dense"``: the full P is stored and every step is one fp64 tensor-core GEMM.
+    ``form="factor"``: nothing but the Markov factors is stored; every step contracts them
+    mode by mode for all columns at once (same results to rounding, any grid size)."""
+    if form not in ("dense", "factor"):
+        raise ValueError("form must be 'dense' or 'factor'")
     ctx = ctx or Context.default()
     kind = MODEL_GCY if hasattr(model, "ρ_ππ") else MODEL_SSY
     fac = Factors.build(kind, model.params, shapes, ctx)
     h = C.c_void_p()
-    check(lib.sdfs_op_from_factors(ctx.handle, fac.handle, STORAGE_DENSE_REPLICATED, C.byref(h)), ctx.handle)
-    return WCOperator(ctx, h, shapes, keep=[fac])
+    storage = STORAGE_DENSE_REPLICATED if form == "dense" else STORAGE_KRON
+    check(lib.sdfs_op_from_factors(ctx.handle, fac.handle, storage, C.byref(h)), ctx.handle)
+    op = WCOperator(ctx, h, shapes, keep=[fac])
+    check(lib.sdfs_sweep_set_form(h, SWEEP_DENSE if form == "dense" else SWEEP_FACTOR), ctx.handle)
+    return op
 
 
 def column_slice(B, nranks, rank):

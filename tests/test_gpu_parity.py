@@ -675,3 +675,40 @@ def test_factor_form_large_axes_every_tile_count_vs_oracle():
     ws, k = S.successive_approx(op, w, tol=0.0, max_iter=3, verbose=False)      # loop-kernel variants
     ref = kop.T(kop.T(kop.T(w)))
     np.testing.assert_allclose(np.asarray(ws), ref, rtol=1e-11)
+
+
+@pytest.mark.parametrize("model,shapes", [("ssy", (4, 7, 6, 5)), ("ssy", (13, 5, 14, 3)), ("gcy", (2, 3, 2, 3, 2, 3))])
+def test_sweep_factor_form_matches_dense_form_and_oracle(model, shapes):
+    """form="factor" (Markov factors contracted mode by mode for all columns at once, no P stored)
+    against form="dense" (the tensor-core GEMM) and the oracle: T panel, per-column SA counts,
+    Newton outer counts and fixed points."""
+    if model == "ssy":
+        mk, OM, OK, disc = S.SSY, O.SSY, O.KronSSY, O.discretize_ssy
+        prefs = np.array([[8.89, 1.97, 0.999], [5.0, 1.3, 0.997], [12.0, 2.0, 0.999], [7.3, 1.61, 0.998],
+                          [10.0, 1.5, 0.9985]])
+    else:
+        mk, OM, OK, disc = S.GCY, O.GCY, O.KronGCY, O.discretize_gcy
+        prefs = np.array([[13.01, 1.5, 0.9987], [9.0, 1.8, 0.998], [11.0, 1.4, 0.9985]])
+    arrays = disc(OM(), shapes)
+    opd = S.make_sweep_operator(mk(), shapes, form="dense")
+    opf = S.make_sweep_operator(mk(), shapes, form="factor")
+    rng = np.random.default_rng(11)
+    W = 300 + 600 * rng.random((len(prefs),) + shapes)
+    gd = np.asarray(S.sweep_apply_T(opd, prefs, W))
+    gf = np.asarray(S.sweep_apply_T(opf, prefs, W))
+    np.testing.assert_allclose(gf, gd, rtol=1e-12)
+    for b, (γ, ψ, β) in enumerate(prefs):
+        np.testing.assert_allclose(gf[b], OK(shapes, OM(γ=γ, ψ=ψ, β=β).params, arrays).T(W[b]), rtol=RTOL_T)
+    Wd, itd, _ = S.sweep_solve(opd, prefs, tol=1e-5)
+    Wf, itf, ef = S.sweep_solve(opf, prefs, tol=1e-5)
+    assert np.all(np.abs(np.asarray(itd) - np.asarray(itf)) <= 1), (itd, itf)
+    np.testing.assert_allclose(np.asarray(Wf), np.asarray(Wd), rtol=1e-9)
+    assert np.all(np.asarray(ef) <= 1e-5)
+    Nd, kd, _ = S.sweep_solve(opd, prefs, algorithm="newton", tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12)
+    Nf, kf, _ = S.sweep_solve(opf, prefs, algorithm="newton", tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12)
+    assert list(kd) == list(kf)
+    np.testing.assert_allclose(np.asarray(Nf), np.asarray(Nd), rtol=1e-9)
+    for b, (γ, ψ, β) in enumerate(prefs):
+        kop = OK(shapes, OM(γ=γ, ψ=ψ, β=β).params, arrays)
+        wn = np.asarray(Nf)[b]
+        assert np.max(np.abs(kop.T(wn) - wn)) < 1e-7 * np.max(wn)
