@@ -310,12 +310,12 @@ int launch_kron_mode(sdfs_ctx *ctx, const KronView &kv, int m, const double *in,
     static const int kron_tc_threads = getenv("SDFS_KRON_THREADS") ? atoi(getenv("SDFS_KRON_THREADS")) : 256;
     static const int kron_tc_ctas = getenv("SDFS_KRON_CTAS") ? atoi(getenv("SDFS_KRON_CTAS")) : 2;
     const KronMode &md = kv.modes[m];
-    // tensor-core contraction (n >= 12): 8 warps per CTA, each on tiles of 8 fibres, one contiguous
+    // tensor-core contraction (n >= KRON_TC_MIN): 8 warps per CTA, each on tiles of 8 fibres, one contiguous
     // tile range per CTA; register-tiled FMA contraction (short axes): one fibre per thread,
     // work items dealt round-robin (any grid size is valid)
     const int nm = kv.shape[md.dim];
     const long long fibres = md.Fcount * md.Mcount;
-    const bool tc = nm >= 12 && nm <= KRON_NMAX_LIMIT;
+    const bool tc = nm >= KRON_TC_MIN && nm <= KRON_NMAX_LIMIT;
     const int threads = tc ? kron_tc_threads : (fibres >= (long long)ctx->sm_count * 128 ? 128 : 64);
     const int grid = tc ? ctx->sm_count * kron_tc_ctas : ctx->sm_count * 6;
     k_kron_mode<<<grid, threads, 0, ctx->stream>>>(kv, m, in, out);

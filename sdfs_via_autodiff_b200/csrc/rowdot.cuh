@@ -376,6 +376,7 @@ __device__ __forceinline__ void kron_mode_pass(const KronView &kv, int m, const 
 // function serves plain launches and the persistent loop kernels.
 // ---------------------------------------------------------------------------
 #define KRON_NMAX_LIMIT 64
+#define KRON_TC_MIN 9        // shortest axis contracted on the tensor cores (two 8-row output tiles)
 template <int NMAX, class Sink>
 __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const double *in, double *smat /* n*NMAX */,
                                                 Sink &&sink) {
@@ -436,7 +437,7 @@ __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const
 }
 
 // ---------------------------------------------------------------------------
-// Tensor-core mode contraction (DMMA m8n8k4) for 12 <= n <= 64.
+// Tensor-core mode contraction (DMMA m8n8k4) for KRON_TC_MIN <= n <= 64.
 // One mode is the GEMM  out[f, i] = sum_k in[f, k] M[i, k]  over the fibres f that share the factor
 // matrix M (n x n).  A warp owns a tile of 8 fibres: the A fragments are the fibre values themselves
 // (lane l holds in[fibre l/4][k0 + l%4], read straight from global: for the innermost axis that is
@@ -573,7 +574,7 @@ template <bool PREFETCH = false, class Sink>
 __device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const double *in, double *smat, Sink &&sink) {
     const int n = kv.shape[kv.modes[m].dim];
     if (n <= 8) kron_mode_fibre<8>(kv, m, in, smat, sink);
-    else if (n < 12) kron_mode_fibre<16>(kv, m, in, smat, sink);
+    else if (n < KRON_TC_MIN) kron_mode_fibre<16>(kv, m, in, smat, sink);
     else if (n <= KRON_NMAX_LIMIT) {
         const int it_n = (n + 7) >> 3;          // 2..8 output tiles
         if constexpr (PREFETCH) {               // stand-alone kernels: exact tile count

@@ -352,7 +352,7 @@ def test_sweep_batched_T_and_solve():
     arrays = O.discretize_ssy(base, shapes)          # P does not depend on (γ, ψ, β)
     prefs = np.array([[8.89, 1.97, 0.999], [5.0, 1.3, 0.997], [12.0, 2.0, 0.999], [7.3, 1.61, 0.998],
                       [10.0, 1.5, 0.9985]])
-    op = S.make_sweep_operator(S.SSY(), shapes)
+    op = S.make_sweep_operator(S.SSY(), shapes, form="dense")
     rng = np.random.default_rng(11)
     W = 300 + 600 * rng.random((len(prefs),) + shapes)
     got = np.asarray(S.sweep_apply_T(op, prefs, W))
@@ -363,7 +363,7 @@ def test_sweep_batched_T_and_solve():
     # ragged sizes: N = 120 (one partial row tile), B = 3 (partial column tile)
     shapes = (2, 3, 4, 5)
     arrays = O.discretize_ssy(base, shapes)
-    op = S.make_sweep_operator(S.SSY(), shapes)
+    op = S.make_sweep_operator(S.SSY(), shapes, form="dense")
     Wd, iters, errs = S.sweep_solve(op, prefs[:3], w_init=800.0, tol=1e-7)
     Wn = np.asarray(Wd)
     for b, (γ, ψ, β) in enumerate(prefs[:3]):
@@ -379,7 +379,7 @@ def test_sweep_batched_T_and_solve():
     # Newton mode: batched BiCGSTAB, one GEMM per Krylov mat-vec of all columns
     shapes = (4, 7, 6, 5)
     arrays = O.discretize_ssy(base, shapes)
-    op = S.make_sweep_operator(S.SSY(), shapes)
+    op = S.make_sweep_operator(S.SSY(), shapes, form="dense")
     Wd, iters, errs, info = S.sweep_solve(op, prefs, algorithm="newton", return_info=True)
     Wt, it_t, _ = S.sweep_solve(op, prefs, algorithm="newton", tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12)
     for b, (γ, ψ, β) in enumerate(prefs):
@@ -400,7 +400,7 @@ def test_sweep_gcy_columns():
     base = O.GCY()
     arrays = O.discretize_gcy(base, shapes)
     prefs = np.array([[13.01, 1.5, 0.9987], [9.0, 1.8, 0.998], [11.0, 1.4, 0.9985]])
-    op = S.make_sweep_operator(S.GCY(), shapes)
+    op = S.make_sweep_operator(S.GCY(), shapes, form="dense")
     rng = np.random.default_rng(3)
     W = 300 + 400 * rng.random((3,) + shapes)
     got = np.asarray(S.sweep_apply_T(op, prefs, W))

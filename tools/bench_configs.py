@@ -134,7 +134,7 @@ if "c4" in which:
 
 if "c5" in which:
     shapes = (10,) * 4
-    op = S.make_sweep_operator(S.SSY(), shapes)
+    op = S.make_sweep_operator(S.SSY(), shapes, form="dense")
     N = op.N
     g = np.linspace(5, 12, 16); p = np.linspace(1.3, 2.0, 16); b = np.linspace(0.997, 0.999, 16)
     lattice = np.array([[gi, pi, bi] for gi in g for pi in p for bi in b])

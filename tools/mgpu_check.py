@@ -73,19 +73,20 @@ from sdfs_via_autodiff_b200.dist import TorchExchange
 shapes = (4, 7, 6, 5)
 arrays = O.discretize_ssy(ssy, shapes)
 prefs = np.array([[8.89, 1.97, 0.999], [5.0, 1.3, 0.997], [12.0, 2.0, 0.999], [7.3, 1.61, 0.998], [10.0, 1.5, 0.9985]])
-sop = S.make_sweep_operator(S.SSY(), shapes, ctx=ctx)
-Wall, its, errs = S.sweep_solve(sop, prefs, algorithm="newton", tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12,
-                                exchange=TorchExchange(dist))
-good = Wall.shape == (len(prefs),) + shapes
-for b, (γ, ψ, β) in enumerate(prefs):
-    m = O.SSY(γ=γ, ψ=ψ, β=β)
-    kop = O.KronSSY(shapes, m.params, arrays)
-    w_ref, _ = O.newton_solver(kop.T, np.full(shapes, 800.0), jvp=kop.jvp, bicgstab_atol=1e-11, verbose=False)
-    w_ref, _ = O.successive_approx(kop.T, w_ref, tol=1e-11, verbose=False)
-    good = good and np.allclose(Wall[b], w_ref, rtol=1e-10)
-report("sweep (newton) sharded over columns", good, f"outer iters {list(its)}")
-Wsa, its_sa, _ = S.sweep_solve(sop, prefs[:3], algorithm="successive_approx", tol=1e-6, exchange=TorchExchange(dist))
-report("sweep (SA) sharded over columns", Wsa.shape[0] == 3 and np.isfinite(Wsa).all(), f"iters {list(its_sa)}")
+for form in ("dense", "factor"):
+    sop = S.make_sweep_operator(S.SSY(), shapes, ctx=ctx, form=form)
+    Wall, its, errs = S.sweep_solve(sop, prefs, algorithm="newton", tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12,
+                                    exchange=TorchExchange(dist))
+    good = Wall.shape == (len(prefs),) + shapes
+    for b, (γ, ψ, β) in enumerate(prefs):
+        m = O.SSY(γ=γ, ψ=ψ, β=β)
+        kop = O.KronSSY(shapes, m.params, arrays)
+        w_ref, _ = O.newton_solver(kop.T, np.full(shapes, 800.0), jvp=kop.jvp, bicgstab_atol=1e-11, verbose=False)
+        w_ref, _ = O.successive_approx(kop.T, w_ref, tol=1e-11, verbose=False)
+        good = good and np.allclose(Wall[b], w_ref, rtol=1e-10)
+    report(f"sweep[{form}] (newton) sharded over columns", good, f"outer iters {list(its)}")
+    Wsa, its_sa, _ = S.sweep_solve(sop, prefs[:3], algorithm="successive_approx", tol=1e-6, exchange=TorchExchange(dist))
+    report(f"sweep[{form}] (SA) sharded over columns", Wsa.shape[0] == 3 and np.isfinite(Wsa).all(), f"iters {list(its_sa)}")
 flag = [ok]
 allok = [None] * world
 dist.all_gather_object(allok, ok)

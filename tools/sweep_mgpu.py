@@ -15,11 +15,12 @@ ctx = S.Context(local)
 S.Context._default = ctx
 sd.init_comm(ctx, rank, world, dist, max_N=120000)
 shapes = (10,) * 4
-op = S.make_sweep_operator(S.SSY(), shapes, ctx=ctx)
+form = "dense" if "--dense" in sys.argv else "factor"
+op = S.make_sweep_operator(S.SSY(), shapes, ctx=ctx, form=form)
 g = np.linspace(5, 12, 16); p = np.linspace(1.3, 2.0, 16); b = np.linspace(0.997, 0.999, 16)
 lattice = np.array([[gi, pi, bi] for gi in g for pi in p for bi in b])
 ex = TorchExchange(dist)
-out = {"world": world, "sets": len(lattice), "shapes": shapes}
+out = {"world": world, "sets": len(lattice), "shapes": shapes, "form": form}
 for algo, kw in (("newton", {}), ("successive_approx", {})):
     if algo == "successive_approx" and "--sa" not in sys.argv:
         continue

@@ -4,7 +4,7 @@ import numpy as np
 import sdfs_via_autodiff_b200 as S
 ctx = S.Context.default()
 shapes = (10,) * 4
-op = S.make_sweep_operator(S.SSY(), shapes)
+op = S.make_sweep_operator(S.SSY(), shapes, form="dense")
 g = np.linspace(5, 12, 16); p = np.linspace(1.3, 2.0, 16); b = np.linspace(0.997, 0.999, 16)
 lattice = np.array([[gi, pi, bi] for gi in g for pi in p for bi in b])
 for B in (512, 4096):
