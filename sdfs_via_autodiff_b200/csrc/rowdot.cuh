@@ -566,6 +566,106 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const 
     }
 }
 
+// Short axes (9 <= n <= 16, two output tiles): a tile is only ~6 DMMAs, so the loop is bound by the
+// latency of its 3-4 fragment loads.  TP tiles per warp iteration, all their loads issued before the
+// first DMMA, keep TP x more bytes in flight (batched sweep panels, N = 10^4 x 4096 columns:
+// 0.31 -> 0.1x ms per mode).
+template <int IT, int TP, class Sink>
+__device__ __forceinline__ void kron_mode_dmma_multi(const KronView &kv, int m, const double *in, double *smat, Sink &&sink) {
+    constexpr int PITCH = 8 * IT + 4, KT = 2 * IT;
+    const KronMode &md = kv.modes[m];
+    const int n = kv.shape[md.dim];
+    const int kt_n = (n + 3) >> 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const long long tpm = (md.Fcount + 7) >> 3;
+    const long long T = md.Mcount * tpm;
+    const long long t_begin = T * blockIdx.x / gridDim.x, t_end = T * (blockIdx.x + 1) / gridDim.x;
+    const long long kstride = md.stride;
+    const bool small_f = md.Fcount < (1LL << 31);
+    int cur_mat = -1;
+    for (long long seg = t_begin; seg < t_end;) {
+        const long long mc = seg / tpm;
+        const long long seg_end = (mc + 1) * tpm < t_end ? (mc + 1) * tpm : t_end;
+        long long rem = mc, mbase = 0;
+        int mat = 0;
+        for (int a = md.nM - 1; a >= 0; --a) {
+            const int c = (int)(rem % md.Mshape[a]);
+            rem /= md.Mshape[a];
+            mat += c * md.Mmat[a];
+            mbase += c * md.Mstride[a];
+        }
+        if (mat != cur_mat) {
+            __syncthreads();
+            const double *msrc = md.mat + (long long)mat * n * n;
+            for (int e = threadIdx.x; e < IT * 8 * PITCH; e += blockDim.x) {
+                const int i = e / PITCH, j = e - i * PITCH;
+                smat[e] = (i < n && j < n) ? msrc[i * n + j] : 0.0;
+            }
+            __syncthreads();
+            cur_mat = mat;
+        }
+        const double *brow = smat + g * PITCH + q;
+        for (long long t = seg + warp; t < seg_end; t += (long long)nwarps * TP) {
+            double a[TP][KT];
+            long long base[TP];
+            bool fv[TP];
+#pragma unroll
+            for (int u = 0; u < TP; ++u) {
+                const long long tt = t + (long long)u * nwarps;
+                const long long f = (tt - mc * tpm) * 8 + g;
+                fv[u] = tt < seg_end && f < md.Fcount;
+                base[u] = mbase;
+                if (small_f) {
+                    unsigned r2 = fv[u] ? (unsigned)f : 0u;
+                    for (int ax = md.nF - 1; ax >= 0; --ax) {
+                        const unsigned sh = (unsigned)md.Fshape[ax], qd = r2 / sh;
+                        base[u] += (long long)(r2 - qd * sh) * md.Fstride[ax];
+                        r2 = qd;
+                    }
+                } else {
+                    long long r2 = fv[u] ? f : 0;
+                    for (int ax = md.nF - 1; ax >= 0; --ax) {
+                        const int c = (int)(r2 % md.Fshape[ax]);
+                        r2 /= md.Fshape[ax];
+                        base[u] += c * md.Fstride[ax];
+                    }
+                }
+                const double *p = in + base[u] + q * kstride;
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) {
+                    a[u][kt] = (fv[u] && kt * 4 + q < n) ? *p : 0.0;
+                    p += 4 * kstride;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < TP; ++u) {
+                double c[IT][2];
+#pragma unroll
+                for (int it = 0; it < IT; ++it) c[it][0] = c[it][1] = 0.0;
+#pragma unroll
+                for (int kt = 0; kt < KT; ++kt) {
+                    if (kt < KT - 1 || kt < kt_n) {          // n >= 9: at least KT - 1 = 3 k steps
+#pragma unroll
+                        for (int it = 0; it < IT; ++it) dmma884(c[it][0], c[it][1], a[u][kt], brow[it * 8 * PITCH + kt * 4]);
+                    }
+                }
+                if (fv[u]) {
+                    long long idx = base[u] + 2 * q * kstride;
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) {
+                        const int i = it * 8 + 2 * q;
+                        if (i < n) sink(idx, c[it][0]);
+                        if (i + 1 < n) sink(idx + kstride, c[it][1]);
+                        idx += 8 * kstride;
+                    }
+                }
+            }
+        }
+        seg = seg_end;
+    }
+}
+
 // dispatch on the size of the contracted axis: register-tiled FMA kernel for short axes, the
 // tensor-core contraction up to 64, the cached-load pass beyond
 // (PREFETCH: software-pipelined fragment loads, +32 registers - for the stand-alone mode kernels;
@@ -579,7 +679,7 @@ __device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const
         const int it_n = (n + 7) >> 3;          // 2..8 output tiles
         if constexpr (PREFETCH) {               // stand-alone kernels: exact tile count
             switch (it_n) {
-            case 2: kron_mode_dmma<2, true>(kv, m, in, smat, sink); break;
+            case 2: kron_mode_dmma_multi<2, 4>(kv, m, in, smat, sink); break;
             case 3: kron_mode_dmma<3, true>(kv, m, in, smat, sink); break;
             case 4: kron_mode_dmma<4, true>(kv, m, in, smat, sink); break;
             case 5: kron_mode_dmma<5, true>(kv, m, in, smat, sink); break;
@@ -588,7 +688,7 @@ __device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const
             default: kron_mode_dmma<8, true>(kv, m, in, smat, sink); break;
             }
         } else {                                // loop kernels: even tile counts (zero-padded rows)
-            if (it_n <= 2) kron_mode_dmma<2, false>(kv, m, in, smat, sink);
+            if (it_n <= 2) kron_mode_dmma_multi<2, 4>(kv, m, in, smat, sink);
             else if (it_n <= 4) kron_mode_dmma<4, false>(kv, m, in, smat, sink);
             else if (it_n <= 6) kron_mode_dmma<6, false>(kv, m, in, smat, sink);
             else kron_mode_dmma<8, false>(kv, m, in, smat, sink);

@@ -226,9 +226,10 @@ struct SweepWork {
     bool factor_form = false;
     KronView kb{};                                          // factor view with a leading column axis
     int64_t ldw = 0;
+    cudaStream_t stream = nullptr;
     void free_all() {
         void *ps[] = {hl, sc, mz, gamma, theta, beta, last_err, err_bits, iters, done, n_active, V, Wa, Wb, T0, T1};
-        for (void *p : ps) if (p) cudaFree(p);
+        for (void *p : ps) if (p) cudaFreeAsync(p, stream);     // stream-ordered pool (cudaMallocAsync)
         hl = sc = mz = gamma = theta = beta = last_err = V = Wa = Wb = T0 = T1 = nullptr;
         err_bits = nullptr; iters = nullptr; done = n_active = nullptr;
     }
@@ -239,13 +240,14 @@ static int sweep_setup(sdfs_op *op, const double *h_prefs, int64_t B, bool panel
     sdfs_ctx *ctx = op->ctx;
     if (!op->factors || (op->storage != SDFS_STORAGE_DENSE && op->storage != SDFS_STORAGE_KRON))
         return sdfs_set_error(ctx, SDFS_ERR_ARG, "sweep needs an operator built from factors");
+    w->stream = ctx->stream;
     w->factor_form = op->storage == SDFS_STORAGE_KRON || op->sweep_form == SDFS_SWEEP_FACTOR;
     if (!w->factor_form && (op->dv.row_begin != 0 || op->dv.row_end != op->dv.N))
         return sdfs_set_error(ctx, SDFS_ERR_ARG, "sweep needs the full P on this rank (columns, not rows, are sharded)");
     const int64_t N = op->kv.N;
     w->ldw = round_up(N, 64);
     const sdfs_factors *f = op->factors;
-    CUDA_TRY(ctx, cudaMalloc(&w->hl, N * 8)); CUDA_TRY(ctx, cudaMalloc(&w->sc, N * 8)); CUDA_TRY(ctx, cudaMalloc(&w->mz, N * 8));
+    CUDA_TRY(ctx, cudaMallocAsync(&w->hl, N * 8, ctx->stream)); CUDA_TRY(ctx, cudaMallocAsync(&w->sc, N * 8, ctx->stream)); CUDA_TRY(ctx, cudaMallocAsync(&w->mz, N * 8, ctx->stream));
     const double *h_lam = (f->model == SDFS_MODEL_SSY) ? f->d_arr[0] : f->d_arr[13];
     const double *sig_c = (f->model == SDFS_MODEL_SSY) ? f->d_arr[8] : f->d_arr[9];
     const double *z = (f->model == SDFS_MODEL_SSY) ? f->d_arr[6] : f->d_arr[0];
@@ -258,9 +260,9 @@ static int sweep_setup(sdfs_op *op, const double *h_prefs, int64_t B, bool panel
         if (psi == 1.0 || g[b] == 1.0) return sdfs_set_error(ctx, SDFS_ERR_ARG, "column %lld: psi and gamma must differ from 1", (long long)b);
         th[b] = (1.0 - g[b]) / (1.0 - 1.0 / psi);
     }
-    CUDA_TRY(ctx, cudaMalloc(&w->gamma, B * 8)); CUDA_TRY(ctx, cudaMalloc(&w->theta, B * 8)); CUDA_TRY(ctx, cudaMalloc(&w->beta, B * 8));
-    CUDA_TRY(ctx, cudaMalloc(&w->last_err, B * 8)); CUDA_TRY(ctx, cudaMalloc(&w->err_bits, B * 8));
-    CUDA_TRY(ctx, cudaMalloc(&w->iters, B * 8)); CUDA_TRY(ctx, cudaMalloc(&w->done, B * 4)); CUDA_TRY(ctx, cudaMalloc(&w->n_active, 4));
+    CUDA_TRY(ctx, cudaMallocAsync(&w->gamma, B * 8, ctx->stream)); CUDA_TRY(ctx, cudaMallocAsync(&w->theta, B * 8, ctx->stream)); CUDA_TRY(ctx, cudaMallocAsync(&w->beta, B * 8, ctx->stream));
+    CUDA_TRY(ctx, cudaMallocAsync(&w->last_err, B * 8, ctx->stream)); CUDA_TRY(ctx, cudaMallocAsync(&w->err_bits, B * 8, ctx->stream));
+    CUDA_TRY(ctx, cudaMallocAsync(&w->iters, B * 8, ctx->stream)); CUDA_TRY(ctx, cudaMallocAsync(&w->done, B * 4, ctx->stream)); CUDA_TRY(ctx, cudaMallocAsync(&w->n_active, 4, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(w->gamma, g.data(), B * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(w->theta, th.data(), B * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(w->beta, be.data(), B * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -271,10 +273,10 @@ static int sweep_setup(sdfs_op *op, const double *h_prefs, int64_t B, bool panel
     const int nb = (int)B;
     CUDA_TRY(ctx, cudaMemcpyAsync(w->n_active, &nb, 4, cudaMemcpyHostToDevice, ctx->stream));
     const size_t pbytes = (size_t)B * w->ldw * 8;
-    CUDA_TRY(ctx, cudaMalloc(&w->V, pbytes));
+    CUDA_TRY(ctx, cudaMallocAsync(&w->V, pbytes, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(w->V, 0, pbytes, ctx->stream));
     if (w->factor_form) {
-        CUDA_TRY(ctx, cudaMalloc(&w->T0, pbytes)); CUDA_TRY(ctx, cudaMalloc(&w->T1, pbytes));
+        CUDA_TRY(ctx, cudaMallocAsync(&w->T0, pbytes, ctx->stream)); CUDA_TRY(ctx, cudaMallocAsync(&w->T1, pbytes, ctx->stream));
         // every mode gains the column index as its outermost free axis (stride ldw): all B columns
         // go through one launch per mode
         w->kb = op->kv;
@@ -289,7 +291,7 @@ static int sweep_setup(sdfs_op *op, const double *h_prefs, int64_t B, bool panel
         }
     }
     if (panels) {
-        CUDA_TRY(ctx, cudaMalloc(&w->Wa, pbytes)); CUDA_TRY(ctx, cudaMalloc(&w->Wb, pbytes));
+        CUDA_TRY(ctx, cudaMallocAsync(&w->Wa, pbytes, ctx->stream)); CUDA_TRY(ctx, cudaMallocAsync(&w->Wb, pbytes, ctx->stream));
         CUDA_TRY(ctx, cudaMemsetAsync(w->Wa, 0, pbytes, ctx->stream));
         CUDA_TRY(ctx, cudaMemsetAsync(w->Wb, 0, pbytes, ctx->stream));
     }
@@ -727,11 +729,11 @@ extern "C" int sdfs_sweep_solve_newton(sdfs_op *op, const double *h_prefs, int64
     SwnState st{};
     int64_t gemms = 0;
     if (rc == SDFS_OK) {
-        cudaError_t e = cudaMalloc(&pan, 12 * pdoubles * sizeof(double));
+        cudaError_t e = cudaMallocAsync(&pan, 12 * pdoubles * sizeof(double), ctx->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(pan, 0, 12 * pdoubles * sizeof(double), ctx->stream);
-        if (e == cudaSuccess) e = cudaMalloc(&sca, 7 * B * sizeof(double));
-        if (e == cudaSuccess) e = cudaMalloc(&lls, 3 * B * sizeof(long long));
-        if (e == cudaSuccess) e = cudaMalloc(&ints, (3 * B + 2) * sizeof(int));
+        if (e == cudaSuccess) e = cudaMallocAsync(&sca, 7 * B * sizeof(double), ctx->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&lls, 3 * B * sizeof(long long), ctx->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&ints, (3 * B + 2) * sizeof(int), ctx->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(sca, 0, 7 * B * sizeof(double), ctx->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(lls, 0, 3 * B * sizeof(long long), ctx->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(ints, 0, (3 * B + 2) * sizeof(int), ctx->stream);
@@ -806,10 +808,10 @@ extern "C" int sdfs_sweep_solve_newton(sdfs_op *op, const double *h_prefs, int64
         if (total_gemms) *total_gemms = gemms;
     }
     cudaStreamSynchronize(ctx->stream);
-    if (pan) cudaFree(pan);
-    if (sca) cudaFree(sca);
-    if (lls) cudaFree(lls);
-    if (ints) cudaFree(ints);
+    if (pan) cudaFreeAsync(pan, ctx->stream);     // stream-ordered pool: the next sweep reuses the blocks
+    if (sca) cudaFreeAsync(sca, ctx->stream);
+    if (lls) cudaFreeAsync(lls, ctx->stream);
+    if (ints) cudaFreeAsync(ints, ctx->stream);
     w.free_all();
     return rc;
 }
