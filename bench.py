@@ -28,7 +28,10 @@ import time
 
 import numpy as np
 
-# stdout carries exactly one JSON line: NCCL's banner / debug output (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+# stdout carries exactly one JSON line.  NCCL prints its version banner to stdout when NCCL_DEBUG=VERSION (set on
+# the GPU boxes) and honours NCCL_DEBUG_FILE only above that level: raise it to WARN and send the log to stderr.
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
