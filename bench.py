@@ -275,6 +275,9 @@ def run_ours(args, shapes):
     solve = None
     if not args.no_solve:
         w0 = ctx.full(shapes, 800.0)
+        # one untimed outer iteration: first launch of the cooperative loop kernel (module load, function
+        # attributes, first peer stores into freshly mapped IPC memory) is a one-off 0.1-0.5 s
+        S.newton_solver(op, w0, tol=1e-8, max_iter=1, verbose=False)
         barrier()
         t0 = time.perf_counter()
         ws, k, info = S.newton_solver(op, w0, tol=1e-8, verbose=False, return_info=True)
@@ -284,7 +287,8 @@ def run_ours(args, shapes):
         solve = {"algo": "newton+bicgstab(device), reference stopping rule (inner atol 1e-4)", "tol": 1e-8, "seconds": dt,
                  "outer_iters": int(k), "inner_iters": [int(x) for x in info["inner_iters"]],
                  "operator_applications": int(info["matvecs"]), "max_abs_Tw_minus_w": res,
-                 "apps_per_s": info["matvecs"] / dt}
+                 "apps_per_s": info["matvecs"] / dt,
+                 "warmup": "one untimed outer iteration (first launch of the loop kernel)"}
         # the reference's rule stops when BiCGSTAB returns its zero start (||Tw-w||_2 <= 1e-4); a solve that
         # really reaches max|Tw-w| <= 1e-8 needs a tighter inner tolerance:
         barrier()
