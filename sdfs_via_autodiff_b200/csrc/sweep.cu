@@ -57,7 +57,9 @@ __global__ void k_sweep_prologue(int64_t N, int64_t B, int64_t ldw, const double
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t b = e / N, k = e % N;
         const double th = sc.theta[b];
-        V[b * ldw + k] = exp(th * h_lam[k]) * pow(W[b * ldw + k], th);
+        // exp(theta h) w^theta as one exponential: 1 log + 1 exp instead of exp + pow (relative error
+        // <= |theta (h + log w)| ulp ~ 1e-14, shrunk again by the 1/theta power of the epilogue)
+        V[b * ldw + k] = exp(th * (h_lam[k] + log(W[b * ldw + k])));
     }
 }
 
@@ -350,11 +352,13 @@ __global__ void __launch_bounds__(256) k_sweep_epi_ew(int64_t N, int64_t ldw, co
     const double omg = 1.0 - g, inv_th = 1.0 / th;
     double emax = 0.0;
     for (int64_t n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
+        // log-domain form of the GEMM epilogue: log(a_row S) = log S + (1/2)((1-gamma) sigma_c)^2 + (1-gamma)(mu_c + z),
+        // so T needs one log and one exp per element instead of two exp and a pow
         const double t2 = omg * sig_c[n];
-        const double a_row = exp(0.5 * (t2 * t2)) * exp(omg * mz[n]);
+        const double la = 0.5 * (t2 * t2) + omg * mz[n];        // log a_row
         const double w_old = ep.W[b * ldw + n];
-        const double sv = a_row * Sb[n];
-        double y = 1.0 + be * pow(sv, inv_th);
+        const double ls = log(Sb[n]) + la;                      // log(a_row S); NaN for S < 0 as pow would give
+        double y = 1.0 + be * exp(inv_th * ls);
         if (ep.mode == 0) {
             if (frozen) y = w_old;
             ep.out0[b * ldw + n] = y;
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(256) k_sweep_epi_ew(int64_t N, int64_t ldw, co
             emax = (d != d || emax != emax) ? d + emax : fmax(emax, d);   // NaN propagates
         } else {
             ep.out0[b * ldw + n] = y - w_old;
-            ep.out1[b * ldw + n] = be * pow(sv, (1.0 - th) * inv_th) * a_row;
+            ep.out1[b * ldw + n] = be * exp((1.0 - th) * inv_th * ls + la);
         }
     }
     if (ep.mode == 0 && ep.err_bits) {
