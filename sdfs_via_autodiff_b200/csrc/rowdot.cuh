@@ -376,7 +376,8 @@ __device__ __forceinline__ void kron_mode_pass(const KronView &kv, int m, const 
 // function serves plain launches and the persistent loop kernels.
 // ---------------------------------------------------------------------------
 #define KRON_NMAX_LIMIT 64
-#define KRON_TC_MIN 9        // shortest axis contracted on the tensor cores (two 8-row output tiles)
+#define KRON_TC_MIN 9        // shortest axis contracted on the tensor cores (two 8-row output tiles);
+                             // kron_mode_fibre<8> serves everything below, so this must stay <= 9
 template <int NMAX, class Sink>
 __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const double *in, double *smat /* n*NMAX */,
                                                 Sink &&sink) {
@@ -673,8 +674,7 @@ __device__ __forceinline__ void kron_mode_dmma_multi(const KronView &kv, int m, 
 template <bool PREFETCH = false, class Sink>
 __device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const double *in, double *smat, Sink &&sink) {
     const int n = kv.shape[kv.modes[m].dim];
-    if (n <= 8) kron_mode_fibre<8>(kv, m, in, smat, sink);
-    else if (n < KRON_TC_MIN) kron_mode_fibre<16>(kv, m, in, smat, sink);
+    if (n < KRON_TC_MIN) kron_mode_fibre<8>(kv, m, in, smat, sink);      // n <= 8
     else if (n <= KRON_NMAX_LIMIT) {
         const int it_n = (n + 7) >> 3;          // 2..8 output tiles
         if constexpr (PREFETCH) {               // stand-alone kernels: exact tile count
