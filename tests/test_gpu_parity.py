@@ -712,3 +712,24 @@ def test_sweep_factor_form_matches_dense_form_and_oracle(model, shapes):
         kop = OK(shapes, OM(γ=γ, ψ=ψ, β=β).params, arrays)
         wn = np.asarray(Nf)[b]
         assert np.max(np.abs(kop.T(wn) - wn)) < 1e-7 * np.max(wn)
+
+
+def test_factor_form_axes_longer_than_64_use_the_cached_load_pass():
+    """Axes beyond the tensor-core tile limit (n > 64) fall back to kron_mode_pass; mixed with a
+    tensor-core axis and short axes in one operator, stand-alone and inside the loop kernels."""
+    shapes = (66, 3, 10, 70)
+    mdl = O.SSY()
+    arrays = O.discretize_ssy(mdl, shapes)
+    kop = O.KronSSY(shapes, mdl.params, arrays)
+    op = S.make_T_ssy(mdl, shapes, arrays, storage="kron")
+    rng = np.random.default_rng(5)
+    w = 500 + 400 * rng.random(shapes)
+    v = rng.standard_normal(shapes)
+    np.testing.assert_allclose(np.asarray(op(w)), kop.T(w), rtol=RTOL_T)
+    np.testing.assert_allclose(np.asarray(op.jvp(w, v)), kop.jvp(w, v), rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(np.asarray(op.apply_P(np.ones(shapes))), 1.0, rtol=0, atol=1e-12)
+    ws, k = S.successive_approx(op, w, tol=0.0, max_iter=5, verbose=False)
+    ref = w.copy()
+    for _ in range(5):
+        ref = kop.T(ref)
+    np.testing.assert_allclose(np.asarray(ws), ref, rtol=1e-11)
