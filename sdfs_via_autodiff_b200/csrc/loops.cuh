@@ -221,7 +221,7 @@ struct DenseLoopOp {
 };
 
 struct KronLoopOp {
-    static constexpr int kMinBlocks = 1;
+    static constexpr int kMinBlocks = 2;     // <= 112 registers: two 288-thread CTAs (18 warps) per SM hide the fragment-load latency
     KronView kv;
     double *tmp0, *tmp1;
     __host__ __device__ size_t dyn_smem() const { return KRON_SMAT_DOUBLES * sizeof(double); }
