@@ -19,7 +19,8 @@ def _gpu_count():
         return 0
 
 
-def test_row_sharded_operator_and_fused_loops_two_ranks():
+@pytest.mark.parametrize("fused", ["1", "0"])      # single applications: peer-store exchange | NCCL all-gather
+def test_row_sharded_operator_and_fused_loops_two_ranks(fused):
     if _gpu_count() < 2:
         pytest.skip("needs 2 GPUs")
     s = socket.socket()
@@ -29,6 +30,7 @@ def test_row_sharded_operator_and_fused_loops_two_ranks():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(ROOT, "tools", "mgpu_check.py")],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+                       capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=dict(os.environ, SDFS_FUSED_EXCHANGE=fused))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "ALL PASS" in r.stdout and "FAIL" not in r.stdout, r.stdout[-3000:]
