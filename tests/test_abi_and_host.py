@@ -97,3 +97,18 @@ def test_host_loglinear_factory_matches_reference_golden(golden_dir):
         got = [f(tuple(x)) for x in rec["points"]]
         np.testing.assert_allclose(got, rec["values"], rtol=1e-9)
         assert set(f.coeffs) >= {"A0", "Ah_λ", "Ah_c", "Ah_z", "Az", "qbar"}
+
+
+def test_sweep_front_end_argument_checks():
+    """Host-side validation happens before any device call (runs without a GPU)."""
+    with pytest.raises(ValueError):
+        S.make_sweep_operator(S.SSY(), (2, 3, 4, 5), form="gemm")
+    from sdfs_via_autodiff_b200.sweep import column_slice, _prefs
+    # column sharding covers every column exactly once, ragged tails included
+    for B, G in ((4096, 8), (5, 2), (3, 8), (1, 1)):
+        got = [column_slice(B, G, r) for r in range(G)]
+        assert got[0][0] == 0 and got[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+    with pytest.raises(ValueError):
+        _prefs(np.ones((3, 2)))
+    assert _prefs([[8.89, 1.97, 0.999]]).shape == (1, 3)
