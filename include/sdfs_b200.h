@@ -231,7 +231,12 @@ int sdfs_sweep_set_form(sdfs_op *op, int form);
 
 /* ---- multi-GPU (one process per GPU) -------------------------------------
  * Row-sharded dense operators: rank g owns rows [N g/G, N (g+1)/G) of P and the
- * full vectors; one all-gather of the result slice per application.
+ * full vectors; one exchange of the result slices per application.  Every rank must issue
+ * the same sequence of operator / solver calls (collective semantics).  Once the arenas are
+ * mapped (sdfs_comm_arena_*), single-output applications (T, JVP, P x) and the solver loops
+ * exchange through NVLink peer stores inside the kernel; without them, and for two-output
+ * applications (SDF), the slices are all-gathered with NCCL.  A rank that never arrives makes
+ * the others return SDFS_ERR_TIMEOUT after ~30 s instead of hanging.
  * sdfs_comm_unique_id fills a 128-byte NCCL id on rank 0; the host distributes
  * it (any transport) and every rank calls sdfs_comm_init. */
 int sdfs_comm_unique_id(void *h_id128);
@@ -239,9 +244,9 @@ int sdfs_comm_init(sdfs_ctx *ctx, int rank, int nranks, const void *h_id128);
 int sdfs_comm_rank(sdfs_ctx *ctx, int *rank, int *nranks);
 int sdfs_comm_allgather_f64(sdfs_ctx *ctx, double *d_buf, int64_t count_per_rank);
 int sdfs_comm_barrier(sdfs_ctx *ctx);
-/* Peer-memory exchange for the fused solver loops: every rank exports a 64-byte
- * IPC handle of its exchange arena, the host all-gathers them, every rank maps
- * its peers. */
+/* Peer-memory exchange (fused applications and solver loops): every rank exports a 64-byte
+ * IPC handle of its exchange arena (sized for operators with N <= max_N), the host all-gathers
+ * them, every rank maps its peers. */
 int sdfs_comm_arena_export(sdfs_ctx *ctx, int64_t max_N, void *h_handle64);
 int sdfs_comm_arena_import(sdfs_ctx *ctx, const void *h_handles64_all);
 
