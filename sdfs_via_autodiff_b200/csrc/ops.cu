@@ -307,8 +307,15 @@ static int run_cont(sdfs_op *op, int which, const double *d_w, const double *d_v
 // One mode contraction out = (I x .. x M_m x .. x I) in of a factor-form view (also used by the
 // batched sweep, sweep.cu, on a view with a leading column axis).
 int launch_kron_mode(sdfs_ctx *ctx, const KronView &kv, int m, const double *in, double *out) {
-    static const int kron_tc_threads = getenv("SDFS_KRON_THREADS") ? atoi(getenv("SDFS_KRON_THREADS")) : 256;
-    static const int kron_tc_ctas = getenv("SDFS_KRON_CTAS") ? atoi(getenv("SDFS_KRON_CTAS")) : 2;
+    // launch shape of the tensor-core contraction; the two environment variables are tuning switches
+    // (profiles/r01_kron_modes.md), clamped to shapes the kernel supports (__launch_bounds__(256))
+    auto env_int = [](const char *name, int dflt, int lo, int hi) {
+        const char *v = getenv(name);
+        const int x = v ? atoi(v) : dflt;
+        return x < lo || x > hi ? dflt : x;
+    };
+    static const int kron_tc_threads = env_int("SDFS_KRON_THREADS", 256, 32, 256) & ~31;
+    static const int kron_tc_ctas = env_int("SDFS_KRON_CTAS", 2, 1, 8);
     const KronMode &md = kv.modes[m];
     // tensor-core contraction (n >= KRON_TC_MIN): 8 warps per CTA, each on tiles of 8 fibres, one contiguous
     // tile range per CTA; register-tiled FMA contraction (short axes): one fibre per thread,
