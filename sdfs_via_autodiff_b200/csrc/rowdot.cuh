@@ -376,16 +376,23 @@ __device__ __forceinline__ void kron_mode_pass(const KronView &kv, int m, const 
 // function serves plain launches and the persistent loop kernels.
 // ---------------------------------------------------------------------------
 #define KRON_NMAX_LIMIT 64
+// Which share of a mode's work items a CTA takes: the launch grid by default, {0, 1} when one CTA
+// contracts a whole (shared-memory resident) vector by itself (fused sweep kernel).
+struct KronShare {
+    unsigned cta, nctas;
+    __device__ __forceinline__ KronShare() : cta(blockIdx.x), nctas(gridDim.x) {}
+    __device__ __forceinline__ KronShare(unsigned c, unsigned n) : cta(c), nctas(n) {}
+};
 #define KRON_TC_MIN 9        // shortest axis contracted on the tensor cores (two 8-row output tiles);
                              // kron_mode_fibre<8> serves everything below, so this must stay <= 9
 template <int NMAX, class Sink>
 __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const double *in, double *smat /* n*NMAX */,
-                                                Sink &&sink) {
+                                                Sink &&sink, KronShare share = KronShare()) {
     const KronMode &md = kv.modes[m];
     const int n = kv.shape[md.dim];
     const long long chunks = (md.Fcount + blockDim.x - 1) / blockDim.x;
     const long long items = md.Mcount * chunks;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    for (long long item = share.cta; item < items; item += share.nctas) {
         const long long mc = item / chunks, chunk = item - mc * chunks;
         // matrix axes -> matrix id and base offset
         long long rem = mc, mbase = 0;
@@ -455,7 +462,8 @@ __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const
 // of the current one.
 // ---------------------------------------------------------------------------
 template <int IT /* 8-row output tiles */, bool PREFETCH, class Sink>
-__device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const double *in, double *smat, Sink &&sink) {
+__device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const double *in, double *smat, Sink &&sink,
+                                               KronShare share = KronShare()) {
     constexpr int PITCH = 8 * IT + 4, KT = 2 * IT;          // n <= 8 IT  =>  ceil(n/4) <= 2 IT
     const KronMode &md = kv.modes[m];
     const int n = kv.shape[md.dim];
@@ -464,7 +472,7 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const 
     const int g = lane >> 2, q = lane & 3;
     const long long tpm = (md.Fcount + 7) >> 3;              // fibre tiles per matrix combination
     const long long T = md.Mcount * tpm;
-    const long long t_begin = T * blockIdx.x / gridDim.x, t_end = T * (blockIdx.x + 1) / gridDim.x;
+    const long long t_begin = T * share.cta / share.nctas, t_end = T * (share.cta + 1) / share.nctas;
     const long long kstride = md.stride;
     const bool small_f = md.Fcount < (1LL << 31);            // 32-bit index decode (always, in practice)
     int cur_mat = -1;
@@ -572,7 +580,8 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const 
 // first DMMA, keep TP x more bytes in flight (batched sweep panels, N = 10^4 x 4096 columns:
 // 0.31 -> 0.1x ms per mode).
 template <int IT, int TP, class Sink>
-__device__ __forceinline__ void kron_mode_dmma_multi(const KronView &kv, int m, const double *in, double *smat, Sink &&sink) {
+__device__ __forceinline__ void kron_mode_dmma_multi(const KronView &kv, int m, const double *in, double *smat, Sink &&sink,
+                                                     KronShare share = KronShare()) {
     constexpr int PITCH = 8 * IT + 4, KT = 2 * IT;
     const KronMode &md = kv.modes[m];
     const int n = kv.shape[md.dim];
@@ -581,7 +590,7 @@ __device__ __forceinline__ void kron_mode_dmma_multi(const KronView &kv, int m, 
     const int g = lane >> 2, q = lane & 3;
     const long long tpm = (md.Fcount + 7) >> 3;
     const long long T = md.Mcount * tpm;
-    const long long t_begin = T * blockIdx.x / gridDim.x, t_end = T * (blockIdx.x + 1) / gridDim.x;
+    const long long t_begin = T * share.cta / share.nctas, t_end = T * (share.cta + 1) / share.nctas;
     const long long kstride = md.stride;
     const bool small_f = md.Fcount < (1LL << 31);
     int cur_mat = -1;
@@ -671,30 +680,34 @@ __device__ __forceinline__ void kron_mode_dmma_multi(const KronView &kv, int m, 
 // tensor-core contraction up to 64, the cached-load pass beyond
 // (PREFETCH: software-pipelined fragment loads, +32 registers - for the stand-alone mode kernels;
 // the persistent loop kernels keep the lean variant)
-template <bool PREFETCH = false, class Sink>
-__device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const double *in, double *smat, Sink &&sink) {
+// (SMALL_FMA: thread-per-fibre FMA contraction up to n = 16 - for vectors resident in shared memory,
+// where coalescing is moot and a warp-wide tile of only 8 fibres costs ~5x the instructions per fibre)
+template <bool PREFETCH = false, bool SMALL_FMA = false, class Sink>
+__device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const double *in, double *smat, Sink &&sink,
+                                                KronShare share = KronShare()) {
     const int n = kv.shape[kv.modes[m].dim];
-    if (n < KRON_TC_MIN) kron_mode_fibre<8>(kv, m, in, smat, sink);      // n <= 8
+    if (SMALL_FMA && n > 8 && n <= 16) { kron_mode_fibre<16>(kv, m, in, smat, sink, share); return; }
+    if (n < KRON_TC_MIN) kron_mode_fibre<8>(kv, m, in, smat, sink, share);      // n <= 8
     else if (n <= KRON_NMAX_LIMIT) {
         const int it_n = (n + 7) >> 3;          // 2..8 output tiles
         if constexpr (PREFETCH) {               // stand-alone kernels: exact tile count
             switch (it_n) {
-            case 2: kron_mode_dmma_multi<2, 4>(kv, m, in, smat, sink); break;
-            case 3: kron_mode_dmma<3, true>(kv, m, in, smat, sink); break;
-            case 4: kron_mode_dmma<4, true>(kv, m, in, smat, sink); break;
-            case 5: kron_mode_dmma<5, true>(kv, m, in, smat, sink); break;
-            case 6: kron_mode_dmma<6, true>(kv, m, in, smat, sink); break;
-            case 7: kron_mode_dmma<7, true>(kv, m, in, smat, sink); break;
-            default: kron_mode_dmma<8, true>(kv, m, in, smat, sink); break;
+            case 2: kron_mode_dmma_multi<2, 4>(kv, m, in, smat, sink, share); break;
+            case 3: kron_mode_dmma<3, true>(kv, m, in, smat, sink, share); break;
+            case 4: kron_mode_dmma<4, true>(kv, m, in, smat, sink, share); break;
+            case 5: kron_mode_dmma<5, true>(kv, m, in, smat, sink, share); break;
+            case 6: kron_mode_dmma<6, true>(kv, m, in, smat, sink, share); break;
+            case 7: kron_mode_dmma<7, true>(kv, m, in, smat, sink, share); break;
+            default: kron_mode_dmma<8, true>(kv, m, in, smat, sink, share); break;
             }
         } else {                                // loop kernels: even tile counts (zero-padded rows)
-            if (it_n <= 2) kron_mode_dmma_multi<2, 4>(kv, m, in, smat, sink);
-            else if (it_n <= 4) kron_mode_dmma<4, false>(kv, m, in, smat, sink);
-            else if (it_n <= 6) kron_mode_dmma<6, false>(kv, m, in, smat, sink);
-            else kron_mode_dmma<8, false>(kv, m, in, smat, sink);
+            if (it_n <= 2) kron_mode_dmma_multi<2, 4>(kv, m, in, smat, sink, share);
+            else if (it_n <= 4) kron_mode_dmma<4, false>(kv, m, in, smat, sink, share);
+            else if (it_n <= 6) kron_mode_dmma<6, false>(kv, m, in, smat, sink, share);
+            else kron_mode_dmma<8, false>(kv, m, in, smat, sink, share);
         }
     }
-    else kron_mode_pass(kv, m, in, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x, sink);
+    else kron_mode_pass(kv, m, in, (int64_t)share.cta * blockDim.x + threadIdx.x, (int64_t)share.nctas * blockDim.x, sink);
 }
 #define KRON_SMAT_DOUBLES (KRON_NMAX_LIMIT * (KRON_NMAX_LIMIT + 4))
 

@@ -13,6 +13,7 @@
 // sup-norm |W' - W| into one atomicMax per (warp, column); converged columns are frozen
 // on the device, the host polls one flag every 64 steps.
 #include "common.cuh"
+#include "rowdot.cuh"      // factor-form mode contractions (fused sweep kernel)
 
 #define TRY(x) do { int _rc = (x); if (_rc != SDFS_OK) return _rc; } while (0)
 
@@ -217,6 +218,24 @@ __global__ void k_state_vectors(int model, KronView kv, const double *__restrict
     }
 }
 
+// dynamic shared memory of k_sweep_fused: the resident N-vector + the largest factor matrix the lean
+// contraction variants stage (rows 8 IT, pitch 8 IT + 4 with IT = 2, 4, 6, 8; 8 x 8 for the FMA kernel).
+// Axes longer than 64 use the cached-load pass, which is not in-place safe: no fused path (returns 0).
+static inline int64_t sweep_fused_ldn(int64_t N) { return (N + 1) & ~(int64_t)1; }
+static inline size_t sweep_fused_smem(const KronView &kv) {
+    size_t smat = 64;
+    for (int m = 0; m < kv.n_modes; ++m) {
+        const int n = kv.shape[kv.modes[m].dim];
+        if (n > KRON_NMAX_LIMIT) return 0;
+        if (n >= KRON_TC_MIN) {
+            const int it = ((n + 7) / 8 + 1) & ~1;          // even tile count of the lean variants
+            const size_t need = (size_t)(8 * it) * (8 * it + 4);
+            if (need > smat) smat = need;
+        }
+    }
+    return (size_t)(sweep_fused_ldn(kv.N) + smat) * sizeof(double);
+}
+
 struct SweepWork {
     double *hl = nullptr, *sc = nullptr, *mz = nullptr;     // per-state base vectors (N)
     double *gamma = nullptr, *theta = nullptr, *beta = nullptr, *last_err = nullptr;   // per column (B)
@@ -226,6 +245,7 @@ struct SweepWork {
     double *V = nullptr, *Wa = nullptr, *Wb = nullptr;      // panels [B][ldw]
     double *T0 = nullptr, *T1 = nullptr;                    // factor form: mode ping-pong panels
     bool factor_form = false;
+    bool fused = false;                                     // factor form with the column resident in shared memory
     KronView kb{};                                          // factor view with a leading column axis
     int64_t ldw = 0;
     cudaStream_t stream = nullptr;
@@ -277,7 +297,14 @@ static int sweep_setup(sdfs_op *op, const double *h_prefs, int64_t B, bool panel
     const size_t pbytes = (size_t)B * w->ldw * 8;
     CUDA_TRY(ctx, cudaMallocAsync(&w->V, pbytes, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(w->V, 0, pbytes, ctx->stream));
-    if (w->factor_form) {
+    {
+        int max_optin = 0;
+        CUDA_TRY(ctx, cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+        static const bool fused_allowed = !(getenv("SDFS_SWEEP_FUSED") && atoi(getenv("SDFS_SWEEP_FUSED")) == 0);
+        const size_t fs = sweep_fused_smem(op->kv);
+        w->fused = w->factor_form && fused_allowed && fs > 0 && fs + 1024 <= (size_t)max_optin;
+    }
+    if (w->factor_form && !w->fused) {
         CUDA_TRY(ctx, cudaMallocAsync(&w->T0, pbytes, ctx->stream)); CUDA_TRY(ctx, cudaMallocAsync(&w->T1, pbytes, ctx->stream));
         // every mode gains the column index as its outermost free axis (stride ldw): all B columns
         // go through one launch per mode
@@ -411,7 +438,137 @@ static int sweep_factor(sdfs_op *op, SweepWork &w, int64_t B, const double *V, c
     return SDFS_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Fused factor-form application for grids whose state vector fits in shared memory (BASELINE config 5:
+// N = 10 000 -> 80 KB).  One CTA per parameter column keeps the column resident: (optional prologue) ->
+// every mode contraction IN PLACE in shared memory (a contraction maps each fibre onto itself and a
+// tile loads all its inputs before it stores, so no second buffer is needed; same tensor-core tiles as
+// k_kron_mode, the CTA taking the whole tile range) -> epilogue.  A column is read once and written
+// once per application instead of once per mode; two CTAs per SM overlap one column's global loads with
+// the other's contractions.  Columns that have converged (SA) cost one copy.
+// ---------------------------------------------------------------------------
+#define SWF_THREADS 256
+#define SWF_UNROLL 8            // independent global loads in flight per thread in the load / epilogue loops
+__global__ void __launch_bounds__(SWF_THREADS, 2)
+k_sweep_fused(const __grid_constant__ KronView kv, int64_t ldw, int64_t ldn, const double *__restrict__ in_panel, int prologue,
+              const double *__restrict__ h_lam, const double *__restrict__ sig_c, const double *__restrict__ mz,
+              SweepEpi ep, SweepCols sc) {
+    extern __shared__ __align__(16) double fsm[];
+    const int64_t N = kv.N;
+    double *cur = fsm, *smat = fsm + ldn;
+    const int64_t b = blockIdx.x;
+    const double th = sc.theta[b];
+    const int frozen = (ep.mode == 0 && sc.done) ? sc.done[b] : 0;
+    const int64_t step = (int64_t)SWF_UNROLL * blockDim.x;
+    if (frozen) {                                   // converged column: W' = W, error 0
+        for (int64_t n = threadIdx.x; n < N; n += blockDim.x) ep.out0[b * ldw + n] = ep.W[b * ldw + n];
+        return;
+    }
+    const double *col = in_panel + b * ldw;
+    for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {
+        double v[SWF_UNROLL], h[SWF_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SWF_UNROLL; ++u) {
+            const int64_t n = n0 + (int64_t)u * blockDim.x;
+            v[u] = n < N ? col[n] : 1.0;
+            h[u] = (prologue && n < N) ? h_lam[n] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < SWF_UNROLL; ++u) {
+            const int64_t n = n0 + (int64_t)u * blockDim.x;
+            if (n < N) cur[n] = prologue ? exp(th * (h[u] + log(v[u]))) : v[u];   // exp(theta h) w^theta, as k_sweep_prologue
+        }
+    }
+    __syncthreads();
+    for (int m = 0; m < kv.n_modes; ++m) {
+        kron_mode_apply<false, true>(kv, m, cur, smat, [&](int64_t idx, double s) { cur[idx] = s; }, KronShare(0, 1));
+        __syncthreads();
+    }
+    // epilogue on the resident contraction (same arithmetic as k_sweep_epi_ew)
+    if (ep.mode == 2) {
+        for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {
+            double d[SWF_UNROLL], vs[SWF_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SWF_UNROLL; ++u) {
+                const int64_t n = n0 + (int64_t)u * blockDim.x;
+                d[u] = n < N ? ep.D[b * ldw + n] : 0.0;
+                vs[u] = n < N ? ep.Vsub[b * ldw + n] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < SWF_UNROLL; ++u) {
+                const int64_t n = n0 + (int64_t)u * blockDim.x;
+                if (n < N) ep.out0[b * ldw + n] = d[u] * cur[n] - vs[u];
+            }
+        }
+        return;
+    }
+    const double g = sc.gamma[b], be = sc.beta[b];
+    const double omg = 1.0 - g, inv_th = 1.0 / th;
+    double emax = 0.0;
+    for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {
+        double wo[SWF_UNROLL], sg[SWF_UNROLL], zz[SWF_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SWF_UNROLL; ++u) {
+            const int64_t n = n0 + (int64_t)u * blockDim.x;
+            wo[u] = n < N ? ep.W[b * ldw + n] : 0.0;
+            sg[u] = n < N ? sig_c[n] : 0.0;
+            zz[u] = n < N ? mz[n] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < SWF_UNROLL; ++u) {
+            const int64_t n = n0 + (int64_t)u * blockDim.x;
+            if (n >= N) continue;
+            const double t2 = omg * sg[u];
+            const double la = 0.5 * (t2 * t2) + omg * zz[u];
+            const double ls = log(cur[n]) + la;
+            const double y = 1.0 + be * exp(inv_th * ls);
+            if (ep.mode == 0) {
+                ep.out0[b * ldw + n] = y;
+                const double dd = fabs(y - wo[u]);
+                emax = (dd != dd || emax != emax) ? dd + emax : fmax(emax, dd);   // NaN propagates
+            } else {
+                ep.out0[b * ldw + n] = y - wo[u];
+                ep.out1[b * ldw + n] = be * exp((1.0 - th) * inv_th * ls + la);
+            }
+        }
+    }
+    if (ep.mode == 0 && ep.err_bits) {
+        __shared__ double red[SWF_THREADS / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, emax, o);
+            emax = (other != other || emax != emax) ? other + emax : fmax(emax, other);
+        }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = emax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double e = red[0];
+            for (int i = 1; i < (int)(blockDim.x >> 5); ++i) e = (red[i] != red[i] || e != e) ? red[i] + e : fmax(e, red[i]);
+            atomicMax(ep.err_bits + b, (unsigned long long)__double_as_longlong(fabs(e)));
+        }
+    }
+}
+
+static int sweep_fused(sdfs_op *op, SweepWork &w, int64_t B, const double *in_panel, int prologue, const SweepEpi &ep,
+                       const SweepCols &sc) {
+    sdfs_ctx *ctx = op->ctx;
+    const size_t smem = sweep_fused_smem(op->kv);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
+    if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
+    k_sweep_fused<<<(unsigned)B, SWF_THREADS, smem, ctx->stream>>>(op->kv, w.ldw, sweep_fused_ldn(op->kv.N), in_panel, prologue, w.hl, w.sc,
+                                                                  w.mz, ep, sc);
+    if (prof) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
+        ctx->prof_used += 2;
+    }
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SDFS_OK;
+}
+
 static inline int sweep_PV(sdfs_op *op, SweepWork &w, int64_t B, const double *V, const SweepEpi &ep, const SweepCols &sc) {
+    if (w.fused) return sweep_fused(op, w, B, V, 0, ep, sc);
     return w.factor_form ? sweep_factor(op, w, B, V, ep, sc) : sweep_gemm(op, w, B, V, ep, sc);
 }
 
@@ -424,9 +581,10 @@ static int sweep_step(sdfs_op *op, SweepWork &w, int64_t B, const double *Win, d
     sdfs_ctx *ctx = op->ctx;
     const int64_t N = op->kv.N;
     SweepCols sc{w.gamma, w.theta, w.beta, track ? w.done : nullptr};
+    SweepEpi ep{0, Win, Wout, nullptr, nullptr, nullptr, track ? w.err_bits : nullptr};
+    if (w.fused) return sweep_fused(op, w, B, Win, 1, ep, sc);         // prologue fused: reads W itself
     k_sweep_prologue<<<panel_grid(ctx, N * B), 256, 0, ctx->stream>>>(N, B, w.ldw, w.hl, Win, sc, w.V);
     ctx->launches++;
-    SweepEpi ep{0, Win, Wout, nullptr, nullptr, nullptr, track ? w.err_bits : nullptr};
     return sweep_PV(op, w, B, w.V, ep, sc);
 }
 
