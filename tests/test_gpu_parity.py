@@ -677,7 +677,8 @@ def test_factor_form_large_axes_every_tile_count_vs_oracle():
     np.testing.assert_allclose(np.asarray(ws), ref, rtol=1e-11)
 
 
-@pytest.mark.parametrize("model,shapes", [("ssy", (4, 7, 6, 5)), ("ssy", (13, 5, 14, 3)), ("gcy", (2, 3, 2, 3, 2, 3))])
+@pytest.mark.parametrize("model,shapes", [("ssy", (4, 7, 6, 5)), ("ssy", (13, 5, 14, 3)), ("gcy", (2, 3, 2, 3, 2, 3)),
+                                          ("ssy", (20, 3, 18, 2)), ("ssy", (40, 2, 3, 33))])
 def test_sweep_factor_form_matches_dense_form_and_oracle(model, shapes):
     """form="factor" (Markov factors contracted mode by mode for all columns at once, no P stored)
     against form="dense" (the tensor-core GEMM) and the oracle: T panel, per-column SA counts,
@@ -706,7 +707,7 @@ def test_sweep_factor_form_matches_dense_form_and_oracle(model, shapes):
     assert np.all(np.asarray(ef) <= 1e-5)
     Nd, kd, _ = S.sweep_solve(opd, prefs, algorithm="newton", tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12)
     Nf, kf, _ = S.sweep_solve(opf, prefs, algorithm="newton", tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12)
-    assert list(kd) == list(kf)
+    assert np.all(np.abs(np.asarray(kd) - np.asarray(kf)) <= 1), (kd, kf)     # borderline stops may differ by one
     np.testing.assert_allclose(np.asarray(Nf), np.asarray(Nd), rtol=1e-9)
     for b, (γ, ψ, β) in enumerate(prefs):
         kop = OK(shapes, OM(γ=γ, ψ=ψ, β=β).params, arrays)
@@ -760,3 +761,22 @@ def test_factor_form_random_shapes_against_oracle():
         np.testing.assert_allclose(np.asarray(op.apply_P(np.ones(shapes))), 1.0, rtol=0, atol=1e-12,
                                    err_msg=str((model, shapes)))
         del op
+
+
+def test_sweep_factor_form_beyond_shared_memory_uses_the_batched_mode_launches():
+    """N = 30 576 does not fit the fused kernel's shared memory: the factor-form sweep runs one launch per
+    mode over the column-batched view.  T panel against the oracle, Newton against single-column solves."""
+    shapes = (14, 13, 12, 14)
+    arrays = O.discretize_ssy(O.SSY(), shapes)
+    prefs = np.array([[8.89, 1.97, 0.999], [5.0, 1.3, 0.997], [12.0, 2.0, 0.999]])
+    op = S.make_sweep_operator(S.SSY(), shapes, form="factor")
+    rng = np.random.default_rng(3)
+    W = 300 + 600 * rng.random((len(prefs),) + shapes)
+    got = np.asarray(S.sweep_apply_T(op, prefs, W))
+    for b, (γ, ψ, β) in enumerate(prefs):
+        np.testing.assert_allclose(got[b], O.KronSSY(shapes, O.SSY(γ=γ, ψ=ψ, β=β).params, arrays).T(W[b]), rtol=RTOL_T)
+    Wn, it, _ = S.sweep_solve(op, prefs, algorithm="newton", tol=1e-9, bicgstab_atol=1e-10, krylov_rtol=1e-12)
+    for b, (γ, ψ, β) in enumerate(prefs):
+        kop = O.KronSSY(shapes, O.SSY(γ=γ, ψ=ψ, β=β).params, arrays)
+        wn = np.asarray(Wn)[b]
+        assert np.max(np.abs(kop.T(wn) - wn)) < 1e-7 * np.max(wn)
