@@ -3,7 +3,6 @@ no SDF code -- formulas from paper/autosdfs.tex:374-384)
 from .solvers import newton_solver, successive_approx
 from .ssy_wc_ratio import make_T_ssy
 from .gcy_wc_ratio import make_T_gcy
-import numpy as np
 
 
 class SDFResult:

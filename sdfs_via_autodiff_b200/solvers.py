@@ -9,11 +9,8 @@ one cooperative CUDA kernel with no host synchronisation per iteration; the
 import ctypes as C
 from textwrap import dedent
 
-import numpy as np
-
 from ._lib import lib, check
-from .device import Context, DeviceArray
-from .operator import WCOperator, resolve_operator
+from .operator import resolve_operator
 
 default_tolerance = 1e-7
 default_max_iter = int(1e6)

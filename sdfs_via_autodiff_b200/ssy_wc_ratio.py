@@ -7,8 +7,7 @@ import time
 
 import numpy as np
 
-from .device import Context
-from .operator import Factors, WCOperator, cached_operator, MODEL_SSY, _Probe, _ProbeResult
+from .operator import Factors, WCOperator, cached_operator, MODEL_SSY
 from .solvers import solver
 from .ssy_model import SSY
 

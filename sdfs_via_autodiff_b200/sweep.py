@@ -14,7 +14,7 @@ import numpy as np
 
 from ._lib import lib, check
 from .device import Context
-from .operator import Factors, WCOperator, MODEL_SSY, MODEL_GCY, STORAGE_DENSE, STORAGE_KRON
+from .operator import Factors, WCOperator, MODEL_SSY, MODEL_GCY, STORAGE_KRON
 
 STORAGE_DENSE_REPLICATED = 2
 SWEEP_DENSE, SWEEP_FACTOR = 0, 1
