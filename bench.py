@@ -40,6 +40,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ssy_T_operator_evals_per_s"
 UNIT = "evals/s"
+# BASELINE.json's metric string, quoted verbatim next to the machine-readable name: its three parts are carried by
+# `value` (evals/s), `time_to_fixed_point` (tol 1e-8) and `roofline` (HBM GB/s vs peak)
+BASELINE_METRIC = "SSY T-operator evals/s & time-to-fixed-point (tol 1e-8); HBM GB/s vs peak"
 DEFAULT_SHAPES = (18, 18, 18, 18)
 
 
@@ -156,7 +159,8 @@ def run_reference(args, shapes):
     # bound the run: each step is `threads` slabs (~0.5 s each single-threaded)
     cb = cpu_reference_form(shapes, args.steps, args.warmup, threads)
     N = int(np.prod(shapes))
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRIC, "baseline_metric": BASELINE_METRIC, "value": cb["value"], "unit": UNIT,
+            "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(shapes, args.gpus),
@@ -323,7 +327,8 @@ def run_ours(args, shapes):
         cpu = cpu_reference_form(shapes, 3, 1, threads)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": METRIC, "baseline_metric": BASELINE_METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(shapes, world), "clocks": clocks, "e2e": e2e,
