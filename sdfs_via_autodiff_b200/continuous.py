@@ -17,7 +17,7 @@ from numpy.polynomial.hermite import hermgauss
 from ._lib import lib, check
 from .device import Context
 from .operator import WCOperator, MODEL_SSY, MODEL_GCY
-from .solvers import solvers as _solver_table, successive_approx as _successive_approx
+from .solvers import solvers as _solver_table, successive_approx as _successive_approx, solver as _solver
 
 
 def _is_gcy(model):
@@ -111,26 +111,54 @@ def make_T_continuous(model, sizes, method="quadrature", d=5, mc_draws=None, mc_
     return grids, T_fun_factory(params, method, model_kind=MODEL_GCY if _is_gcy(model) else MODEL_SSY, ctx=ctx)
 
 
+_GRID_KEYS = {False: ("h_λ_grid_size", "h_c_grid_size", "h_z_grid_size", "z_grid_size"),
+              True: ("h_λ_grid_size", "h_c_grid_size", "h_z_grid_size", "h_zπ_grid_size", "z_grid_size",
+                     "z_π_grid_size")}
+_GRID_DEFAULTS = {False: (10, 10, 10, 20), True: (10, 10, 10, 10, 20, 20)}
+
+
 def wc_ratio_continuous(model, *grid_sizes, num_std_devs=3.2, d=5, mc_draw_size=2000, seed=1234, w_init=None,
                         ram_free=20, tol=1e-5, method="quadrature", algorithm="successive_approx", verbose=True,
-                        write_to_file=False, filename="w_star_data.npy", mc_draws=None):
+                        write_to_file=True, filename="w_star_data.npy", mc_draws=None, solver_tol=None,
+                        **grid_kw):
     """Iterate to convergence on the continuous-state operator and return (grids, w_star).
-    Same keywords as the reference (grid sizes default to 10,10,10,20 for SSY and 10,10,10,10,20,20
-    for GCY; w_init defaults to ones).  ``ram_free`` is accepted for compatibility (no batching is
-    needed); ``tol`` is forwarded to the solver (the reference accepts it but never forwards it);
-    ``write_to_file`` defaults to False here (the reference's two consecutive np.save records are
-    written when it is True)."""
-    if not grid_sizes:
-        grid_sizes = (10, 10, 10, 10, 20, 20) if _is_gcy(model) else (10, 10, 10, 20)
-    grids, T = make_T_continuous(model, grid_sizes, method, d, mc_draws, mc_draw_size, seed, num_std_devs)
+
+    Same signature and defaults as the reference (ssy_wc_ratio_continuous.py:229-297,
+    gcy_wc_ratio_continuous.py:264-335): the grid sizes may be given positionally or with the
+    reference's keyword names (``h_λ_grid_size=...``, ``z_grid_size=...``; GCY adds
+    ``h_zπ_grid_size`` and ``z_π_grid_size``), ``w_init`` defaults to ones, ``write_to_file``
+    defaults to True (two consecutive np.save records).  Like the reference, the solve goes
+    through ``solver(T, w_init, algorithm=algorithm)`` -- the reference accepts ``tol`` but never
+    forwards it, so the effective tolerance is solvers.py's default 1e-7; ``tol`` is accepted and
+    ignored here for the same result.  Extensions: ``solver_tol`` (forwarded to the solver when
+    given), ``verbose`` is honoured, ``mc_draws`` supplies the Monte-Carlo shocks; ``ram_free``
+    is accepted for compatibility (no batching is needed on the device)."""
+    gcy = _is_gcy(model)
+    keys = _GRID_KEYS[gcy]
+    sizes = list(_GRID_DEFAULTS[gcy])
+    if len(grid_sizes) > len(keys):
+        raise TypeError(f"wc_ratio_continuous takes at most {len(keys)} grid sizes for this model")
+    for i, v in enumerate(grid_sizes):
+        sizes[i] = v
+    for k, v in grid_kw.items():
+        if k not in keys:
+            raise TypeError(f"wc_ratio_continuous() got an unexpected keyword argument {k!r}")
+        if keys.index(k) < len(grid_sizes):
+            raise TypeError(f"wc_ratio_continuous() got multiple values for argument {k!r}")
+        sizes[keys.index(k)] = v
+    grids, T = make_T_continuous(model, tuple(int(v) for v in sizes), method, d, mc_draws, mc_draw_size, seed,
+                                 num_std_devs)
     if w_init is None:
         w_init = T.ctx.full(T.shapes, 1.0)
-    try:
-        fn = _solver_table[algorithm]
-    except KeyError:
-        print(f"Algorithm {algorithm} not found.  \nFalling back to successive approximation.\n")
-        fn = _successive_approx
-    w_star, _ = fn(T, w_init, tol=tol, verbose=verbose)
+    if solver_tol is None:
+        w_star = _solver(T, w_init, algorithm=algorithm, verbose=verbose)
+    else:
+        try:
+            fn = _solver_table[algorithm]
+        except KeyError:
+            print(f"Algorithm {algorithm} not found.  \nFalling back to successive approximation.\n")
+            fn = _successive_approx
+        w_star, _ = fn(T, w_init, tol=solver_tol, verbose=verbose)
     if write_to_file:
         save_wstar(filename, grids, w_star)
     return grids, w_star

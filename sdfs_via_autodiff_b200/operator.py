@@ -75,6 +75,7 @@ class Factors:
             a = np.empty(shp, dtype=np.float64)
             assert a.size == n.value
             check(lib.sdfs_d2h(self.ctx.handle, a.ctypes.data, p, a.nbytes), self.ctx.handle)
+            a.flags.writeable = False     # immutable like the reference's device arrays (lets cached_operator memoise digests)
             out.append(a)
         return tuple(out)
 
@@ -219,31 +220,69 @@ class _ProbeResult:
 
 def resolve_operator(f):
     """WCOperator behind ``f`` (an operator, or a closure such as
-    ``lambda w: T_ssy(w, shapes, params, arrays)``), else None."""
+    ``lambda w: T_ssy(w, shapes, params, arrays)``), else None.
+
+    The closure is called once with a probe object.  Only failures caused by the probe itself
+    (a callable that does arithmetic on its argument: TypeError / AttributeError naming the
+    probe) mean "not an operator of this package"; anything raised while the operator is being
+    built or applied (SdfsError: out of memory, CUDA errors; ValueError: wrong array shapes or
+    parameters; MemoryError ...) propagates unchanged."""
     if isinstance(f, WCOperator):
         return f
     try:
         r = f(_Probe())
-    except Exception:
-        return None
+    except (TypeError, AttributeError) as e:
+        if "_Probe" in str(e):
+            return None
+        raise
     return r.op if isinstance(r, _ProbeResult) else None
 
 
 _op_cache = {}
+_digest_cache = {}      # id(array) -> (weakref, shape, digest): hash each factor array once, not per call
+
+
+def _array_digest(a):
+    import weakref
+    if isinstance(a, np.ndarray) and not a.flags.writeable:
+        ent = _digest_cache.get(id(a))
+        if ent is not None and ent[0]() is a:
+            return ent[1]
+    d = hashlib.sha1(np.ascontiguousarray(np.asarray(a, dtype=np.float64)).tobytes()).digest()
+    if isinstance(a, np.ndarray) and not a.flags.writeable:
+        try:
+            key = id(a)
+            _digest_cache[key] = (weakref.ref(a, lambda _r, k=key: _digest_cache.pop(k, None)), d)
+        except TypeError:
+            pass
+    return d
+
+
+class _CachedOperator(WCOperator):
+    """Operator shared through ``cached_operator``: keyed by (shapes, params, arrays), so it
+    must keep computing what that key says -- preferences cannot be changed in place."""
+
+    def set_preferences(self, γ, ψ, β):
+        raise ValueError("this operator is shared through the T_ssy/T_gcy operator cache and is immutable; "
+                         "build a private one with make_T_ssy / make_T_gcy (or WCOperator.from_factors) "
+                         "to change preferences")
 
 
 def cached_operator(model, shapes, params, arrays, storage="auto", ctx=None):
-    """Operator for (shapes, params, arrays), built once per distinct input."""
+    """Operator for (shapes, params, arrays), built once per distinct input.  The discretisers of
+    this package return read-only arrays, whose content digests are remembered, so repeated
+    ``T_ssy(w, shapes, params, arrays)`` calls do not re-hash the factors."""
     ctx = ctx or Context.default()
     h = hashlib.sha1()
     h.update(repr((model, tuple(shapes), tuple(float(p) for p in params), storage, ctx.device)).encode())
     for a in arrays:
-        h.update(np.ascontiguousarray(np.asarray(a, dtype=np.float64)).tobytes())
+        h.update(_array_digest(a))
     key = h.hexdigest()
     op = _op_cache.get(key)
     if op is None:
         fac = Factors.from_host(model, params, shapes, arrays, ctx)
         op = WCOperator.from_factors(fac, storage)
+        op.__class__ = _CachedOperator
         if len(_op_cache) >= 8:
             _op_cache.pop(next(iter(_op_cache)))
         _op_cache[key] = op

@@ -148,5 +148,10 @@ def solver(f, x_init, algorithm="newton", verbose=True):
                """
         print(dedent(msg))
         solver = successive_approx
-    x_star, num_iter = solver(f, x_init)
+    # the reference calls the chosen solver with its defaults only (solvers.py:175: tol and verbose
+    # are not forwarded, so it always prints); verbose is honoured here so callers can silence it
+    if verbose:
+        x_star, num_iter = solver(f, x_init)
+    else:
+        x_star, num_iter = solver(f, x_init, verbose=False)
     return x_star

@@ -66,6 +66,13 @@ def test_solver_front_end_semantics(capsys):
     with pytest.raises(TypeError, match="no CPU fallback"):
         S.newton_solver(f, np.array([0.0]), verbose=False)
     assert set(S.solvers) == {"newton", "anderson", "gd", "successive_approx"}
+    # a failure inside the closure that is not caused by the probe (bad shapes, out of memory, CUDA
+    # errors while the operator is built) propagates instead of being reported as "not an operator"
+
+    def broken(w):
+        raise ValueError("factor array has shape (3,), expected (4,)")
+    with pytest.raises(ValueError, match="factor array has shape"):
+        S.successive_approx(broken, np.array([0.0]), verbose=False)
     # unknown algorithm: the reference's message, then successive approximation (solvers.py:164-172)
     with pytest.raises(TypeError):
         S.solver(f, np.array([0.0]), algorithm="no-such-algo")

@@ -43,6 +43,22 @@ def test_T_gcy_matches_reference_loops(golden_dir, tag, storage):
     np.testing.assert_allclose(got, z["Tw_ref"], rtol=RTOL_T, atol=0)
 
 
+def test_cached_operator_is_shared_and_immutable(golden_dir):
+    """T_ssy(w, shapes, params, arrays) resolves to one cached operator per distinct input; the
+    shared handle cannot be re-parameterised behind the cache key's back."""
+    from sdfs_via_autodiff_b200.operator import cached_operator
+    z, shapes, params, arrays = _load(golden_dir, "ssy_2345")
+    op = cached_operator(MODEL_SSY, shapes, params, arrays)
+    assert cached_operator(MODEL_SSY, shapes, params, arrays) is op
+    with pytest.raises(ValueError, match="immutable"):
+        op.set_preferences(5.0, 1.5, 0.998)
+    private = S.make_T_ssy(params, shapes, arrays)
+    private.set_preferences(5.0, 1.5, 0.998)                # private operators stay mutable
+    ref = O.KronSSY(shapes, O.SSY(γ=5.0, ψ=1.5, β=0.998).params, arrays).T(z["w"])
+    np.testing.assert_allclose(np.asarray(private(z["w"])), ref, rtol=RTOL_T)
+    np.testing.assert_allclose(np.asarray(op(z["w"])), z["Tw_ref"], rtol=RTOL_T)
+
+
 def test_device_discretiser_matches_oracle():
     ssy, gcy = S.SSY(), S.GCY()
     for shapes in ((2, 3, 4, 5), (10, 10, 10, 10), (3, 18, 5, 33)):
@@ -318,6 +334,44 @@ def test_gcy_newton_and_sdf(storage):
     np.testing.assert_allclose(w7, w7_ref, rtol=RTOL_W)
 
 
+@pytest.mark.parametrize("model", ["ssy", "gcy"])
+@pytest.mark.parametrize("storage", ["dense", "kron"])
+def test_sdf_matches_quadrature_of_the_unintegrated_sdf(model, storage):
+    """a13, non-circular: the device q_f (device-built e_sdf, k_build_scalings) against a
+    Gauss-Hermite integration of the paper's un-integrated log M' (oracle/sdf.py::sdf_quadrature,
+    which shares no closed form with the kernels); a perturbed e_sdf on the device is detected."""
+    from oracle import sdf as SD
+    if model == "ssy":
+        ref, shapes = O.SSY(), (2, 3, 4, 5)
+        arrays = O.discretize_ssy(ref, shapes)
+        kop = O.KronSSY(shapes, ref.params, arrays)
+        P, ar, ac, β, θ = O.dense_ssy(shapes, ref.params, arrays)
+        fields = SD.state_fields_ssy(shapes, ref.params, arrays)
+        res = S.solve_ssy(S.SSY(), shapes, algo="newton", storage=storage, tol=1e-9, bicgstab_atol=1e-10,
+                          krylov_rtol=1e-12)
+    else:
+        ref, shapes = O.GCY(), (2, 3, 2, 3, 2, 3)
+        arrays = O.discretize_gcy(ref, shapes)
+        kop = O.KronGCY(shapes, ref.params, arrays)
+        P, ar, ac, β, θ = O.dense_gcy(shapes, ref.params, arrays)
+        fields = SD.state_fields_gcy(shapes, ref.params, arrays)
+        res = S.solve_gcy(S.GCY(), shapes, algo="newton", storage=storage, tol=1e-9, bicgstab_atol=1e-10,
+                          krylov_rtol=1e-12)
+    w = np.asarray(res.w)
+    q_quad, euler_quad = SD.sdf_quadrature(w, P, *fields, β, kop.γ, θ, kop.μ_c)
+    np.testing.assert_allclose(np.asarray(res.q_f).reshape(-1), q_quad, rtol=RTOL_W)
+    assert np.max(np.abs(euler_quad)) < 1e-8          # E[M' R_w'] = 1 from the un-integrated SDF at the device's w*
+    rows = np.array([0, 7, int(np.prod(shapes)) - 1])
+    M = np.asarray(res.sdf_rows(rows))                # rows of Mbar integrate to the quadrature q_f
+    np.testing.assert_allclose((P[rows] * M).sum(1), q_quad[rows], rtol=RTOL_W)
+    if storage == "dense":
+        # teeth: the same pass with a wrong closed form (missing 1/2 in the variance term) is caught
+        es_bad = np.asarray(res.op.device_arrays()[3]) * np.exp(0.5 * (kop.γ * fields[1]) ** 2)
+        bad = S.WCOperator.from_dense(P, ar, ac, β, θ, shapes=shapes, e_sdf=es_bad)
+        q_bad, _ = bad.sdf(w)
+        assert np.max(np.abs(np.asarray(q_bad).reshape(-1) / q_quad - 1)) > 1e-3
+
+
 def test_ssy_10k_states_dense_vs_kron_and_counts():
     """N = 10^4 (0.8 GB dense P): the two device implementations agree with each other and
     with the oracle; SA iteration count of BASELINE.md (8 733 @ 1e-7)."""
@@ -511,7 +565,21 @@ def test_continuous_state_operators():
     np.testing.assert_allclose(np.asarray(Tg(wg)), gref.T(wg), rtol=1e-12)
     np.testing.assert_allclose(np.asarray(Tg.jvp(wg, vg)), gref.jvp(wg, vg), rtol=1e-10, atol=1e-12)
     # the reference's driver surface
-    g2, w2 = S.wc_ratio_continuous(S.SSY(), 4, 5, 6, 7, d=3, algorithm="newton", tol=1e-7, verbose=False)
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "w_star_data.npy")
+        g2, w2 = S.wc_ratio_continuous(S.SSY(), 4, 5, 6, 7, d=3, algorithm="newton", tol=1e-7, verbose=False,
+                                       filename=out)
+        assert os.path.exists(out)                 # write_to_file defaults to True like the reference
+        # the reference's keyword names for the grid sizes; tol is accepted and NOT forwarded (the
+        # reference calls solver(T, w_init, algorithm=...): solvers.py's default 1e-7 applies)
+        g3, w3 = S.wc_ratio_continuous(S.SSY(), h_λ_grid_size=4, h_c_grid_size=5, h_z_grid_size=6, z_grid_size=7,
+                                       d=3, algorithm="newton", tol=1.0, verbose=False, write_to_file=False)
+        np.testing.assert_array_equal(np.asarray(w3), np.asarray(w2))
+        with pytest.raises(TypeError):
+            S.wc_ratio_continuous(S.SSY(), 4, h_λ_grid_size=4, write_to_file=False)
+        with pytest.raises(TypeError):
+            S.wc_ratio_continuous(S.SSY(), h_zπ_grid_size=4, write_to_file=False)
     assert len(g2) == 4 and np.asarray(w2).shape == sizes
     np.testing.assert_allclose(np.asarray(w2), w_fix, rtol=1e-5)
     with pytest.raises(S.SdfsError):

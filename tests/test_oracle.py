@@ -196,6 +196,52 @@ def test_gcy_newton_and_sdf_euler_identity():
     np.testing.assert_allclose((P[rows] * M).sum(1), q_f[rows], rtol=1e-12)
 
 
+def _sdf_case(model):
+    from oracle import sdf as SD
+    if model == "ssy":
+        m, shapes = O.SSY(), (2, 3, 4, 5)
+        arrays = O.discretize_ssy(m, shapes)
+        kop = O.KronSSY(shapes, m.params, arrays)
+        dense = O.dense_ssy(shapes, m.params, arrays)
+        es, fields = SD.e_sdf_ssy(shapes, m.params, arrays), SD.state_fields_ssy(shapes, m.params, arrays)
+    else:
+        m, shapes = O.GCY(), (2, 3, 2, 3, 2, 3)
+        arrays = O.discretize_gcy(m, shapes)
+        kop = O.KronGCY(shapes, m.params, arrays)
+        dense = O.dense_gcy(shapes, m.params, arrays)
+        es, fields = SD.e_sdf_gcy(shapes, m.params, arrays), SD.state_fields_gcy(shapes, m.params, arrays)
+    w, _ = O.newton_solver(kop.T, np.full(shapes, 800.0), jvp=kop.jvp, bicgstab_atol=1e-11, verbose=False)
+    w, _ = O.successive_approx(kop.T, w, tol=1e-12, verbose=False)
+    return kop, dense, es, fields, w
+
+
+@pytest.mark.parametrize("model", ["ssy", "gcy"])
+def test_sdf_closed_form_equals_quadrature_of_the_unintegrated_sdf(model):
+    """Non-circular pin of the SDF (paper/autosdfs.tex:374-384): the closed forms q_f / e_sdf
+    against a Gauss-Hermite integration of the un-integrated log M', and the pricing identity
+    E[M' R_w'] = 1 evaluated from the un-integrated M' at the fixed point of the
+    reference-pinned T.  A wrong sign or a missing 1/2 in e_sdf must be caught."""
+    from oracle import sdf as SD
+    kop, (P, ar, ac, β, θ), es, fields, w = _sdf_case(model)
+    q_f, _ = O.sdf_dense(w, P, ar, ac, es, β, θ)
+    q_quad, euler_quad = SD.sdf_quadrature(w, P, *fields, β, kop.γ, θ, kop.μ_c)
+    np.testing.assert_allclose(q_f, q_quad, rtol=1e-12)
+    assert np.max(np.abs(euler_quad)) < 1e-11
+    # rule is converged: a different node count gives the same integral
+    q_quad2, _ = SD.sdf_quadrature(w, P, *fields, β, kop.γ, θ, kop.μ_c, n_nodes=40)
+    np.testing.assert_allclose(q_quad, q_quad2, rtol=1e-13)
+    # the check has teeth: perturbed closed forms fail it
+    σ_c = fields[1]
+    for bad in (es * np.exp(-(kop.γ * σ_c) ** 2),            # -gamma^2 sigma_c^2 / 2 (wrong sign)
+                es * np.exp(0.5 * (kop.γ * σ_c) ** 2),        # gamma^2 sigma_c^2 (missing 1/2)
+                es * np.exp(2 * kop.γ * (kop.μ_c + fields[0]))):   # +gamma g_c (wrong sign)
+        q_bad, _ = O.sdf_dense(w, P, ar, ac, bad, β, θ)
+        assert np.max(np.abs(q_bad / q_quad - 1)) > 1e-3
+    # away from the fixed point the pricing identity fails (it is not an algebraic identity)
+    _, euler_off = SD.sdf_quadrature(1.01 * w, P, *fields, β, kop.γ, θ, kop.μ_c)
+    assert np.max(np.abs(euler_off)) > 1e-5
+
+
 def test_loglinear_matches_reference_golden(golden_dir):
     """wc_loglinear_factory of the reference (ssy_model.py:86-156, gcy_model.py:80-159), evaluated
     by the importable reference files themselves (tests/golden/make_golden.py)."""
