@@ -55,6 +55,13 @@ def parse():
     ap.add_argument("--shapes", default=",".join(map(str, DEFAULT_SHAPES)))
     ap.add_argument("--no-solve", action="store_true", help="skip the time-to-fixed-point solve")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra.configs block (C1, C3, C4, C5 at N=1)")
+    ap.add_argument("--storage", default="dense", choices=["dense", "kron"],
+                    help="operator storage of the timed steps: dense P (BASELINE configs[1], default) or the "
+                         "factor form (configs[3] sizes, e.g. --shapes 56,56,56,56; leading-axis slabs over the ranks)")
+    ap.add_argument("--cpu-sample-slabs", type=int, default=0,
+                    help="reference arm: time only this many (l,k) slabs per step and scale (labelled fallback; "
+                         "default 0 = every slab of every step)")
     ap.add_argument("--cpu-threads", type=int, default=0)
     return ap.parse_args()
 
@@ -111,9 +118,11 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU legs
-def cpu_reference_form(shapes, steps, warmup, threads):
-    """Oracle restatement of the reference's own N^2 broadcast-and-sum, on a bounded sample:
-    each step evaluates `threads` (l,k) slabs concurrently (NumPy releases the GIL)."""
+def cpu_reference_form(shapes, steps, warmup, threads, sample_slabs=0):
+    """Oracle restatement of the reference's own N^2 broadcast-and-sum (ssy_wc_ratio.py:116-148) on the
+    host cores.  One step = ONE FULL evaluation of T: every (l,k) slab of the grid, `threads` slabs at a
+    time (NumPy releases the GIL), so ms_per_step x steps is the work behind `value`.  With
+    sample_slabs > 0 only that many slabs are evaluated per step and the time is scaled (labelled)."""
     import oracle as O
     from oracle.operators import ssy_broadcast_slab
     from concurrent.futures import ThreadPoolExecutor
@@ -123,32 +132,52 @@ def cpu_reference_form(shapes, steps, warmup, threads):
     L, K = shapes[0], shapes[1]
     slabs = [(l, k) for l in range(L) for k in range(K)]
     threads = max(1, min(threads, len(slabs)))
+    per_step = len(slabs) if sample_slabs <= 0 else min(len(slabs), sample_slabs)
     pool = ThreadPoolExecutor(threads)
     times = []
     pos = 0
+    out = np.empty(shapes)
+
+    def one(lk):
+        out[lk[0], lk[1]] = ssy_broadcast_slab(op, w, *lk)
+
     for it in range(warmup + steps):
-        todo = [slabs[(pos + i) % len(slabs)] for i in range(threads)]
-        pos += threads
+        todo = [slabs[(pos + i) % len(slabs)] for i in range(per_step)]
+        pos += per_step
         t0 = time.perf_counter()
-        list(pool.map(lambda lk: ssy_broadcast_slab(op, w, *lk), todo))
+        list(pool.map(one, todo))
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+        if per_step == len(slabs):
+            w = out.copy()                                     # the steps chain, w <- T w, like the GPU arm
     pool.shutdown()
-    per_eval = np.mean(times) / threads * len(slabs)           # seconds per full T evaluation
-    # factored (sum-factorised) CPU form of the same operator, for the other side of the comparison
-    op.T(w)
+    per_eval = np.mean(times) / per_step * len(slabs)          # seconds per full T evaluation
+    # factored (sum-factorised) CPU form of the same operator: the honest CPU competitor
+    wf = np.full(shapes, 800.0)
+    op.T(wf)
+    nf = max(5, steps)
     t0 = time.perf_counter()
-    for _ in range(5):
-        op.T(w)
-    fact = (time.perf_counter() - t0) / 5
-    return dict(value=1.0 / per_eval, unit=UNIT, cores=threads, kind="port",
-                sample=f"{threads} of {len(slabs)} (l,k) slabs per step x {steps} steps of the reference's "
-                       f"N^2 broadcast-sum (ssy_wc_ratio.py:116-148), scaled to a full evaluation",
-                ms_per_step=float(np.mean(times) * 1e3),
-                factored_evals_per_s=1.0 / fact,
-                factored_note="same oracle, sum-factorised over the Kronecker factors (80 N bytes instead of 8 N^2)",
-                host_cpus=os.cpu_count())
+    for _ in range(nf):
+        wf = op.T(wf)
+    fact = (time.perf_counter() - t0) / nf
+    if per_step == len(slabs):
+        sample = (f"every one of the {len(slabs)} (l,k) slabs per step ({threads} at a time) x {steps} steps: full "
+                  f"evaluations of the reference's N^2 broadcast-sum (ssy_wc_ratio.py:116-148), nothing extrapolated")
+        check = float(np.max(np.abs(out / op.T(np.full(shapes, 800.0)) - 1))) if warmup + steps == 1 else None
+    else:
+        sample = (f"{per_step} of {len(slabs)} (l,k) slabs per step x {steps} steps of the reference's N^2 "
+                  f"broadcast-sum (ssy_wc_ratio.py:116-148), scaled to a full evaluation (sampled fallback)")
+        check = None
+    r = dict(value=1.0 / per_eval, unit=UNIT, cores=threads, kind="port", sample=sample,
+             ms_per_step=float(np.mean(times) * 1e3), full_evaluations=per_step == len(slabs),
+             factored_evals_per_s=1.0 / fact,
+             factored_note="same oracle, sum-factorised over the Kronecker factors (numpy einsum, 80 N bytes "
+                           "instead of 8 N^2): the fastest CPU form of the same T",
+             host_cpus=os.cpu_count())
+    if check is not None:
+        r["broadcast_vs_factored_max_rel"] = check
+    return r
 
 
 def run_reference(args, shapes):
@@ -156,34 +185,255 @@ def run_reference(args, shapes):
     if rank != 0:
         return
     threads = args.cpu_threads or min(os.cpu_count() or 1, 16)
-    # bound the run: each step is `threads` slabs (~0.5 s each single-threaded)
-    cb = cpu_reference_form(shapes, args.steps, args.warmup, threads)
+    cb = cpu_reference_form(shapes, args.steps, args.warmup, threads, args.cpu_sample_slabs)
     N = int(np.prod(shapes))
     line = {"impl": "reference", "metric": METRIC, "baseline_metric": BASELINE_METRIC, "value": cb["value"], "unit": UNIT,
             "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(shapes, args.gpus),
+            "data": "synthetic", "config": workload_config(shapes, args.gpus, args.storage),
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_factored": {"value": cb["factored_evals_per_s"], "unit": UNIT, "cores": "numpy einsum (BLAS threads)",
+                             "note": "second baseline: the sum-factorised CPU form of the same operator"},
             "note": "JAX/jaxopt/quantecon are not installable offline: this is the oracle port of the "
                     "reference arithmetic on host cores (kind=port), N=%d" % N}
     print(json.dumps(line))
 
 
-def workload_config(shapes, gpus):
+def workload_config(shapes, gpus, storage="dense"):
     N = int(np.prod(shapes))
-    tag = "BASELINE configs[1]" if tuple(shapes) == tuple(DEFAULT_SHAPES) else "non-default grid via --shapes"
-    return {"workload": f"SSY {tuple(shapes)} grid, N={N}, dense fp64 P ({8 * N * N / 1e9:.1f} GB) resident in HBM, "
-                        f"w <- T w chained, w0=800 ({tag})",
-            "shapes": list(shapes), "N": N,
-            "parallelism": f"row-shard x{gpus}" if gpus > 1 else "single GPU",
-            "l2": "inputs larger than L2 (P >> 126 MB), no flush needed",
+    if storage == "dense":
+        tag = "BASELINE configs[1]" if tuple(shapes) == tuple(DEFAULT_SHAPES) else "non-default grid via --shapes"
+        return {"workload": f"SSY {tuple(shapes)} grid, N={N}, dense fp64 P ({8 * N * N / 1e9:.1f} GB) resident in HBM, "
+                            f"w <- T w chained, w0=800 ({tag})",
+                "shapes": list(shapes), "N": N, "storage": "dense",
+                "parallelism": f"row-shard x{gpus}" if gpus > 1 else "single GPU",
+                "l2": "inputs larger than L2 (P >> 126 MB), no flush needed",
+                "solver": "newton + on-device BiCGSTAB (reference stopping rule), analytic JVP"}
+    return {"workload": f"SSY {tuple(shapes)} grid, N={N}, factor-form (Kronecker) operator, 80 N = {80 * N / 1e6:.0f} MB "
+                        f"algorithmic bytes per application, w <- T w chained, w0=800 (BASELINE configs[3] sizes via --storage kron)",
+            "shapes": list(shapes), "N": N, "storage": "kron",
+            "parallelism": f"leading-axis slabs x{gpus}, h_lambda contraction first, result slabs exchanged by peer stores"
+                           if gpus > 1 else "single GPU",
+            "l2": ("working set larger than L2" if 16 * N > 126e6 else
+                   "working set fits the 126 MB L2: a 256 MB buffer is overwritten between timed applications"),
             "solver": "newton + on-device BiCGSTAB (reference stopping rule), analytic JVP"}
 
 
 # --------------------------------------------------------------------------- GPU arm
+def _timed_chain(ctx, op, w, reps, flush=None):
+    """reps chained applications w <- T w timed with CUDA events on the launching stream; with `flush`
+    (a DeviceArray larger than L2) each application is timed on its own and the buffer is rewritten
+    in between, outside the timed spans."""
+    if flush is None:
+        ctx.timer_start()
+        for _ in range(reps):
+            w = op(w)
+        return ctx.timer_stop_ms(), w
+    total = 0.0
+    for _ in range(reps):
+        flush.fill(0.0)
+        ctx.timer_start()
+        w = op(w)
+        total += ctx.timer_stop_ms()
+    return total, w
+
+
+def parity_block(S, ctx, op, kop, shapes, dist, rank, world, solve):
+    """Driver-visible correctness at any N: one application of T to a seeded w by the (sharded) timed
+    operator and by the factor-form operator, checked on rank 0 against the oracle's KronSSY.T; every
+    rank must hold the same bytes; Newton outer count against the oracle's own Newton solve."""
+    import hashlib
+    rng = np.random.default_rng(1233)
+    w_seed = np.exp(rng.standard_normal(shapes))
+    got = np.asarray(op(w_seed))
+    got_k = np.asarray(kop(w_seed)) if kop is not None else None
+    digest = hashlib.sha1(got.tobytes() + (got_k.tobytes() if got_k is not None else b"")).hexdigest()
+    identical = True
+    if dist:
+        all_d = [None] * world
+        dist.all_gather_object(all_d, digest)
+        identical = len(set(all_d)) == 1
+    out = None
+    if rank == 0:
+        import oracle as O
+        ssy = O.SSY()
+        ko = O.KronSSY(shapes, ssy.params, O.discretize_ssy(ssy, shapes))
+        ref = ko.T(w_seed)
+        out = {"w": "exp(standard_normal(shapes)), seed 1233", "max_rel_T": float(np.max(np.abs(got / ref - 1))),
+               "max_rel_T_factor_form": float(np.max(np.abs(got_k / ref - 1))) if got_k is not None else None,
+               "ranks_identical": bool(identical), "tolerance": 1e-12, "checker": "oracle.KronSSY.T (NumPy, rank 0)"}
+        if solve is not None and int(np.prod(shapes)) <= 200000:
+            info = {}
+            w_o, k_o = O.newton_solver(ko.T, np.full(shapes, 800.0), jvp=ko.jvp, tol=1e-8, verbose=False)
+            out.update({"newton_outer": int(solve["outer_iters"]), "newton_outer_oracle": int(k_o),
+                        "newton_w_max_rel_vs_oracle": float(np.max(np.abs(solve.pop("_w") / w_o - 1))),
+                        "newton_w_note": "reference stopping rule: both stop at ||Tw-w||_2 <= 1e-4, agreement 1e-5 (SURVEY fact 4)"})
+        elif solve is not None:
+            solve.pop("_w", None)
+            out["newton_outer"] = int(solve["outer_iters"])
+        bad = (out["max_rel_T"] > 1e-12 or (got_k is not None and out["max_rel_T_factor_form"] > 1e-12)
+               or not identical or ("newton_outer_oracle" in out and abs(out["newton_outer"] - out["newton_outer_oracle"]) > 1)
+               or ("newton_w_max_rel_vs_oracle" in out and out["newton_w_max_rel_vs_oracle"] > 1e-5))
+        out["ok"] = not bad
+    return out
+
+
+def extra_configs(S, ctx, peak):
+    """BASELINE configs C1, C3, C4, C5 on one GPU, each with its own parity scalar against the oracle
+    (`value` stays on C2).  Wall clock for whole solves, CUDA events for single applications."""
+    import gc
+    import oracle as O
+    from oracle import sdf as SD
+    cfg = {}
+    rng = np.random.default_rng(1233)
+    # ---- C1: SSY default small grid, successive approximation (the reference's CPU-runnable case)
+    shapes = (2, 3, 4, 5)
+    ssy = O.SSY()
+    ko = O.KronSSY(shapes, ssy.params, O.discretize_ssy(ssy, shapes))
+    op = S.make_T_ssy(S.SSY(), shapes, storage="dense", ctx=ctx)
+    c1 = {"shapes": list(shapes), "N": 120}
+    for tol in (1e-7, 1e-8):
+        S.successive_approx(op, np.full(shapes, 800.0), tol=tol, verbose=False)
+        t0 = time.perf_counter()
+        w, k = S.successive_approx(op, np.full(shapes, 800.0), tol=tol, verbose=False)
+        dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        w_o, k_o = O.successive_approx(ko.T, np.full(shapes, 800.0), tol=tol, verbose=False)
+        dt_o = time.perf_counter() - t0
+        c1[f"sa_tol{tol:g}"] = {"iters": int(k), "iters_oracle": int(k_o), "seconds": dt, "us_per_iter": dt / k * 1e6,
+                                "w_max_rel_vs_oracle": float(np.max(np.abs(np.asarray(w) / w_o - 1))),
+                                "cpu_oracle_factored_seconds": dt_o}
+    c1["ok"] = all(v["iters"] == v["iters_oracle"] and v["w_max_rel_vs_oracle"] < 1e-10
+                   for k_, v in c1.items() if k_.startswith("sa_"))
+    cfg["C1_ssy_default_grid_sa"] = c1
+    del op
+    # ---- C4: factor form at the named sizes
+    c4 = {}
+    flush = ctx.empty((1 << 25,))            # 256 MB > 126 MB L2
+    for shp in ((18,) * 4, (32,) * 4, (56,) * 4):
+        op = S.make_T_ssy(S.SSY(), shp, storage="kron", ctx=ctx)
+        N = op.N
+        w = ctx.full(shp, 800.0)
+        for _ in range(3):
+            w = op(w)
+        ctx.sync()
+        ms_chain, w = _timed_chain(ctx, op, w, 20)
+        ms_chain /= 20
+        ms_flush, w = _timed_chain(ctx, op, w, 10, flush)
+        ms_flush /= 10
+        wn, k, info = S.newton_solver(op, ctx.full(shp, 800.0), verbose=False, return_info=True)   # first launch untimed
+        ctx.sync()
+        t0 = time.perf_counter()
+        wn, k, info = S.newton_solver(op, ctx.full(shp, 800.0), verbose=False, return_info=True)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        w_seed = np.exp(rng.standard_normal(shp))
+        ko4 = O.KronSSY(shp, ssy.params, O.discretize_ssy(ssy, shp))
+        rel = float(np.max(np.abs(np.asarray(op(w_seed)) / ko4.T(w_seed) - 1)))
+        wn_h = np.asarray(wn)
+        res2 = float(np.linalg.norm((ko4.T(wn_h) - wn_h).ravel()))
+        c4["x".join(map(str, shp))] = {
+            "N": N, "T_ms": ms_flush, "T_ms_chained_l2_warm": ms_chain, "algorithmic_bytes": 80 * N,
+            "GBps_80N": 80 * N / ms_flush / 1e6, "frac_80N": 80 * N / ms_flush / 1e6 / peak,
+            "newton_seconds": dt, "newton_outer": int(k), "newton_applications": int(info["matvecs"]),
+            "newton_ms_per_application": dt / info["matvecs"] * 1e3,
+            "T_max_rel_vs_oracle": rel, "newton_residual_l2_by_oracle": res2, "ok": rel < 1e-12 and res2 <= 1.01e-4}
+        del op, w, wn
+        gc.collect()
+    cfg["C4_ssy_factor_form"] = c4
+    # ---- C5: 4096-set (gamma, psi, beta) Newton sweep on SSY (10,)^4, both forms
+    shapes = (10,) * 4
+    g = np.linspace(5, 12, 16); q = np.linspace(1.3, 2.0, 16); b = np.linspace(0.997, 0.999, 16)
+    lattice = np.array([[gi, pi, bi] for gi in g for pi in q for bi in b])
+    arrays10 = O.discretize_ssy(ssy, shapes)
+    c5 = {"shapes": list(shapes), "N": 10000, "sets": 4096}
+    for form in ("factor", "dense"):
+        sop = S.make_sweep_operator(S.SSY(), shapes, ctx=ctx, form=form)
+        S.sweep_solve(sop, lattice[:64], algorithm="newton")            # first launches untimed
+        ctx.sync()
+        t0 = time.perf_counter()
+        W, its, errs, info = S.sweep_solve(sop, lattice, algorithm="newton", return_info=True)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        Wh = np.asarray(W)
+        # parity: the batched T step of three lattice corners against the oracle, and the corner columns'
+        # fixed points against the oracle's residual test
+        cols = [0, 2047, 4095]
+        Wt = np.asarray(S.sweep_apply_T(sop, lattice[cols], Wh[cols]))
+        rel = 0.0
+        res = 0.0
+        for j, c in enumerate(cols):
+            γ, ψ, β = lattice[c]
+            kc = O.KronSSY(shapes, O.SSY(γ=γ, ψ=ψ, β=β).params, arrays10)
+            ref = kc.T(Wh[c])
+            rel = max(rel, float(np.max(np.abs(Wt[j] / ref - 1))))
+            res = max(res, float(np.linalg.norm((ref - Wh[c]).ravel())))
+        r = {"newton_sweep_seconds": dt, "applications": int(info["gemms"]), "outer_min": int(its.min()),
+             "outer_max": int(its.max()), "sets_per_s": 4096 / dt, "T_max_rel_vs_oracle": rel,
+             "corner_residual_l2_by_oracle": res, "ok": rel < 1e-12 and res <= 1.01e-4 and not np.isnan(Wh).any()}
+        if form == "dense":
+            r["tflops_fp64"] = 2.0 * 1e8 * 4096 * info["gemms"] / dt / 1e12
+            r["fp64_peak_tflops_measured"] = 36.97
+            r["fp64_peak_source"] = "tools/pipe_probe.cu (register-only DMMA, profiles/r02_pipe_probe.md)"
+        c5[form] = r
+        del sop, W
+        gc.collect()
+    cfg["C5_ssy_sweep_4096"] = c5
+    # ---- C3: GCY fine grid, dense P (110.7 GB): T, Newton, SDF pass
+    shapes = (7,) * 6
+    gcy = O.GCY()
+    t0 = time.perf_counter()
+    op = S.make_T_gcy(S.GCY(), shapes, storage="dense", ctx=ctx)
+    ctx.sync()
+    build = time.perf_counter() - t0
+    N = op.N
+    w = ctx.full(shapes, 800.0)
+    for _ in range(3):
+        w = op(w)
+    ctx.sync()
+    ctx.prof_enable(10)
+    ms, w = _timed_chain(ctx, op, w, 10)
+    kms, kn = ctx.prof_read()
+    ctx.prof_enable(0)
+    kms /= max(1, kn)
+    S.newton_solver(op, ctx.full(shapes, 800.0), max_iter=1, verbose=False) if False else None
+    t0 = time.perf_counter()
+    wn, k, info = S.newton_solver(op, ctx.full(shapes, 800.0), verbose=False, return_info=True)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    op.sdf(wn)
+    ctx.sync()
+    ctx.timer_start()
+    qf, eu = op.sdf(wn)
+    sms = ctx.timer_stop_ms()
+    arrays = O.discretize_gcy(gcy, shapes)
+    kg = O.KronGCY(shapes, gcy.params, arrays)
+    w_seed = np.exp(rng.standard_normal(shapes))
+    rel = float(np.max(np.abs(np.asarray(op(w_seed)) / kg.T(w_seed) - 1)))
+    wn_h = np.asarray(wn)
+    # SDF parity: q_f = beta^theta e_sdf (w-1)^(1-theta) P(a_col w^(theta-1)) through the oracle's factor form
+    es = SD.e_sdf_gcy(shapes, gcy.params, arrays).reshape(shapes)
+    qf_ref = kg.β ** kg.θ * es * (wn_h - 1) ** (1 - kg.θ) * kg.P_apply(kg.a_col * wn_h ** (kg.θ - 1))
+    rel_q = float(np.max(np.abs(np.asarray(qf) / qf_ref - 1)))
+    cfg["C3_gcy_fine_grid_w_and_sdf"] = {
+        "shapes": list(shapes), "N": N, "dense_P_GB": 8 * N * N / 1e9, "operator_build_s": build,
+        "T_ms": ms / 10, "T_kernel_ms": kms, "T_GBps": (8.0 * N * N + 32 * N) / kms / 1e6,
+        "T_frac_of_hbm_peak": (8.0 * N * N + 32 * N) / kms / 1e6 / peak,
+        "newton_seconds": dt, "newton_outer": int(k), "newton_applications": int(info["matvecs"]),
+        "sdf_pass_ms": sms, "sdf_GBps": (8.0 * N * N + 64 * N) / sms / 1e6,
+        "w_range": [float(wn_h.min()), float(wn_h.max())], "euler_max_abs": float(np.max(np.abs(np.asarray(eu)))),
+        "T_max_rel_vs_oracle": rel, "q_f_max_rel_vs_oracle": rel_q,
+        "newton_residual_l2_by_oracle": float(np.linalg.norm((kg.T(wn_h) - wn_h).ravel())),
+        "ok": rel < 1e-12 and rel_q < 1e-10}
+    del op
+    gc.collect()
+    return cfg
+
+
 def run_ours(args, shapes):
+    import gc
     import sdfs_via_autodiff_b200 as S
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,6 +447,7 @@ def run_ours(args, shapes):
         sd.init_comm(ctx, rank, world, dist, max_N=int(np.prod(shapes)))
     S.Context._default = ctx
     N = int(np.prod(shapes))
+    kron = args.storage == "kron"
 
     def barrier():
         ctx.sync()
@@ -212,10 +463,11 @@ def run_ours(args, shapes):
         return float(t[0])
 
     t0 = time.perf_counter()
-    op = S.make_T_ssy(S.SSY(), shapes, storage="dense", ctx=ctx)      # device discretiser + dense expansion
+    op = S.make_T_ssy(S.SSY(), shapes, storage=args.storage, ctx=ctx)   # device discretiser (+ dense expansion)
     ctx.sync()
     build_s = time.perf_counter() - t0
     nloc = op.row_end - op.row_begin
+    flush = ctx.empty((1 << 25,)) if kron and 16 * N <= 126e6 else None    # L2 flush buffer (256 MB)
 
     w = ctx.full(shapes, 800.0)
     for _ in range(args.warmup):
@@ -227,51 +479,69 @@ def run_ours(args, shapes):
     ctx.prof_enable(args.steps)
     n0 = ctx.launch_count
     barrier()
-    ctx.timer_start()
-    for _ in range(args.steps):
-        w = op(w)
-    ms = ctx.timer_stop_ms()
+    ms, w = _timed_chain(ctx, op, w, args.steps, flush)
     barrier()
-    launches = ctx.launch_count - n0
+    launches = ctx.launch_count - n0 - (args.steps if flush is not None else 0)
     kern_ms, kern_n = ctx.prof_read()
     ctx.prof_enable(0)
     ms = max_over_ranks(ms)
     value = args.steps / (ms / 1e3)
 
-    # ---- e2e through the public API with HOST buffers: h2d(w) -> T -> d2h(Tw) every step
+    # ---- e2e through the public API with HOST buffers.  Every rank needs the full w on its device (h2d of
+    # 8 N bytes per rank per step); the result is identical on every rank after the fused exchange, so each
+    # rank reads back only the slab it computed (the d2h bytes of the job are 8 N per step, not 8 N x ranks)
     w_host = ctx.pinned_empty(shapes)            # page-locked host buffers (cudaMallocHost)
     out_host = ctx.pinned_empty(shapes)
     w_host[...] = 800.0
+    flat_out = out_host.reshape(-1)
+    rb, re = op.row_begin, op.row_end
+
+    def e2e_step(wh, oh):
+        r = op(wh)                               # h2d(w) -> prologue + pass (+ fused exchange)
+        if world == 1:
+            r.numpy(out=oh)
+        else:
+            r.reshape(-1)[rb:re].numpy(out=oh.reshape(-1)[rb:re])      # own slab only
     for _ in range(2):
-        op(w_host).numpy(out=out_host)
-        w_host, out_host = out_host, w_host
+        e2e_step(w_host, out_host)
+    w_host[...] = 800.0
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        op(w_host).numpy(out=out_host)           # h2d(w) -> prologue + dense pass (+ all-gather) -> d2h(Tw)
-        w_host, out_host = out_host, w_host
+        e2e_step(w_host, out_host)
+        if world == 1:
+            w_host, out_host = out_host, w_host  # chained on one GPU; at N > 1 each step re-applies T to the same w
     ctx.sync()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
-    e2e = {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * N,
-           "ms_per_step": e2e_s / args.steps * 1e3}
+    e2e = {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * N * world, "d2h_bytes_per_step": 8 * N,
+           "ms_per_step": e2e_s / args.steps * 1e3,
+           "note": "pinned host w -> device (every rank) -> T -> each rank reads back the slab it owns"}
 
-    # ---- roofline of the dominant kernel (dense row-stream pass), per launch on this rank
+    # ---- roofline of the dominant kernel, per launch on this rank
     peak, peak_src = peaks()
-    alg_bytes = 8.0 * nloc * N + 8.0 * N + 24.0 * nloc      # P rows + x + (a_row, w_out, ...) per row
-    kern_avg_ms = kern_ms / max(1, kern_n)
+    if not kron:
+        alg_bytes = 8.0 * nloc * N + 8.0 * N + 24.0 * nloc      # P rows + x + (a_row, w_out, ...) per row
+        kern_avg_ms = kern_ms / max(1, kern_n)
+        kname = "k_dense_apply<1> (TMA ring, fused T epilogue)"
+    else:
+        alg_bytes = 80.0 * N * nloc / N                          # 80 N per application, this rank's share
+        kern_avg_ms = kern_ms / max(1, kern_n) if kern_n else ms / args.steps
+        kname = "k_kron_apply (one cooperative launch: fused prologue, mode contractions, fused epilogue)"
     achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            if tj.get("shapes") == list(shapes) and tj.get("n_gpus") == world:
-                traffic = tj.get("k_dense_apply_bytes_per_launch")
+            for ent in (tj if isinstance(tj, list) else [tj]):
+                if ent.get("shapes") == list(shapes) and ent.get("n_gpus") == world and ent.get("storage", "dense") == args.storage:
+                    traffic = ent.get("bytes_per_launch", ent.get("k_dense_apply_bytes_per_launch"))
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_dense_apply<1> (TMA ring, fused T epilogue)",
+                "traffic": traffic, "traffic_source": "ncu --set full capture of the same kernel and shapes (profiles/traffic.json)",
+                "kernel": kname,
                 "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n, "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                 "kernel_share_of_step": kern_avg_ms / (ms / args.steps)}
@@ -289,12 +559,14 @@ def run_ours(args, shapes):
         ws, k, info = S.newton_solver(op, w0, tol=1e-8, verbose=False, return_info=True)
         ctx.sync()
         dt = max_over_ranks(time.perf_counter() - t0)
-        res = float(np.max(np.abs(np.asarray(op(ws)) - np.asarray(ws))))
+        ws_h = np.asarray(ws)
+        res = float(np.max(np.abs(np.asarray(op(ws)) - ws_h)))
         solve = {"algo": "newton+bicgstab(device), reference stopping rule (inner atol 1e-4)", "tol": 1e-8, "seconds": dt,
+                 "storage": args.storage,
                  "outer_iters": int(k), "inner_iters": [int(x) for x in info["inner_iters"]],
                  "operator_applications": int(info["matvecs"]), "max_abs_Tw_minus_w": res,
                  "apps_per_s": info["matvecs"] / dt,
-                 "warmup": "one untimed outer iteration (first launch of the loop kernel)"}
+                 "warmup": "one untimed outer iteration (first launch of the loop kernel)", "_w": ws_h}
         # the reference's rule stops when BiCGSTAB returns its zero start (||Tw-w||_2 <= 1e-4); a solve that
         # really reaches max|Tw-w| <= 1e-8 needs a tighter inner tolerance:
         barrier()
@@ -307,37 +579,75 @@ def run_ours(args, shapes):
         solve["tight"] = {"inner_atol": 1e-9, "inner_rtol": 1e-10, "seconds": dtt, "outer_iters": int(kt),
                           "operator_applications": int(it_["matvecs"]), "max_abs_Tw_minus_w": rest}
 
+    # ---- the other storage of the same grid: parity partner, and (dense run) the factor-form numbers
     extra = {}
-    if world == 1:
-        # factor-form operator on the same grid (same T, 80 N algorithmic bytes)
-        kop = S.make_T_ssy(S.SSY(), shapes, storage="kron", ctx=ctx)
+    kop = None
+    if not kron:
+        kop = S.make_T_ssy(S.SSY(), shapes, storage="kron", ctx=ctx)   # leading-axis slabs over the ranks when world > 1
         wk = ctx.full(shapes, 800.0)
         for _ in range(3):
             wk = kop(wk)
-        ctx.sync()
-        ctx.timer_start()
-        for _ in range(50):
-            wk = kop(wk)
-        kms = ctx.timer_stop_ms() / 50
-        extra["factor_form"] = {"evals_per_s": 1e3 / kms, "ms": kms,
-                                "note": "sum-factorised Kronecker apply of the same T (never materialises P)"}
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        threads = args.cpu_threads or min(os.cpu_count() or 1, 16)
-        cpu = cpu_reference_form(shapes, 3, 1, threads)
+        barrier()
+        kms, wk = _timed_chain(ctx, kop, wk, 50)
+        kms = max_over_ranks(kms) / 50
+        extra["factor_form"] = {"evals_per_s": 1e3 / kms, "ms": kms, "frac_80N": 80.0 * N / kms / 1e6 / peak,
+                                "note": "sum-factorised Kronecker apply of the same T (never materialises P), "
+                                        "chained, vectors L2-resident at this size"}
+        if not args.no_solve:
+            S.newton_solver(kop, ctx.full(shapes, 800.0), tol=1e-8, verbose=False)
+            barrier()
+            t0 = time.perf_counter()
+            wk2, kk, ik = S.newton_solver(kop, ctx.full(shapes, 800.0), tol=1e-8, verbose=False, return_info=True)
+            ctx.sync()
+            dk = max_over_ranks(time.perf_counter() - t0)
+            solve["factor_form"] = {"seconds": dk, "outer_iters": int(kk), "operator_applications": int(ik["matvecs"]),
+                                    "max_rel_vs_dense_storage": float(np.max(np.abs(np.asarray(wk2) / solve["_w"] - 1)))}
+    parity = parity_block(S, ctx, op, kop, shapes, dist, rank, world, solve)
+    if solve is not None:
+        solve.pop("_w", None)
 
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu and not kron:
+        threads = args.cpu_threads or min(os.cpu_count() or 1, 16)
+        cpu = cpu_reference_form(shapes, 1, 0, threads)        # ONE full evaluation (every slab), ~80 core-seconds
+        extra["vs_cpu_factored"] = {"value_over_cpu_factored": value / cpu["factored_evals_per_s"],
+                                    "factor_form_over_cpu_factored": extra["factor_form"]["evals_per_s"] / cpu["factored_evals_per_s"],
+                                    "note": "cpu factored = the oracle's sum-factorised NumPy form, the fastest CPU "
+                                            "implementation of the same T on this box"}
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs and not kron:
+        del op, kop, w
+        if 'wk' in dir():
+            del wk
+        gc.collect()
+        try:
+            configs = extra_configs(S, ctx, peak)
+        except Exception as e:        # the headline line must survive a failure in the side block; say so loudly
+            configs = {"error": repr(e)}
+    if configs is not None:
+        extra["configs"] = configs
+
+    rc = 0
     if rank == 0:
         line = {"metric": METRIC, "baseline_metric": BASELINE_METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(shapes, world), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "time_to_fixed_point": solve, "operator_build_s": build_s, **extra}
+                "config": workload_config(shapes, world, args.storage), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+                "time_to_fixed_point": solve, "operator_build_s": build_s, "extra": extra}
         print(json.dumps(line))
+        if parity is not None and not parity["ok"]:
+            sys.stderr.write("PARITY FAILURE: %s\n" % json.dumps(parity))
+            rc = 3
+        if configs and any(isinstance(v, dict) and v.get("ok") is False for v in configs.values()):
+            sys.stderr.write("PARITY FAILURE in extra.configs\n")
+            rc = 3
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
 
 
 def main():

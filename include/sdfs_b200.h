@@ -44,7 +44,8 @@ typedef struct sdfs_factors sdfs_factors; /* discretised model: Markov factor ar
 
 enum { SDFS_MODEL_SSY = 0, SDFS_MODEL_GCY = 1 };
 enum { SDFS_KRYLOV_BICGSTAB = 0, SDFS_KRYLOV_GMRES = 1 };
-enum { SDFS_STORAGE_DENSE = 0, SDFS_STORAGE_KRON = 1, SDFS_STORAGE_DENSE_REPLICATED = 2, SDFS_STORAGE_CONTINUOUS = 3 };
+enum { SDFS_STORAGE_DENSE = 0, SDFS_STORAGE_KRON = 1, SDFS_STORAGE_DENSE_REPLICATED = 2, SDFS_STORAGE_CONTINUOUS = 3,
+       SDFS_STORAGE_KRON_LOCAL = 4 };
 
 /* ---- context ---------------------------------------------------------- */
 int sdfs_abi_version(void);
@@ -121,7 +122,12 @@ int sdfs_op_from_dense(sdfs_ctx *ctx, const double *d_P, int64_t N, int64_t ld,
  * (storage = SDFS_STORAGE_KRON: sum-factorised apply, T_ssy ssy_wc_ratio.py:82-149,
  * T_gcy gcy_wc_ratio.py:134-236).  Dense storage honours the context's rank:
  * each rank materialises only its row slice; SDFS_STORAGE_DENSE_REPLICATED keeps the
- * full P on every rank (parameter sweeps shard columns, not rows). */
+ * full P on every rank (parameter sweeps shard columns, not rows).  Factor-form storage
+ * honours the rank too where the leading axis can be contracted first (SSY, 9 <= shapes[0] <= 64,
+ * shapes[0] >= ranks): each rank owns a slab of the leading axis, i.e. the contiguous rows
+ * sdfs_op_info reports, reads the full input vector and exchanges result rows by peer stores;
+ * other factor-form operators (GCY) and SDFS_STORAGE_KRON_LOCAL stay whole on every rank.
+ * sdfs_op_info reports SDFS_STORAGE_KRON for both. */
 int sdfs_op_from_factors(sdfs_ctx *ctx, sdfs_factors *f, int storage, sdfs_op **out);
 /* Continuous-state operator ("next" row of the scope table): the T of
  * ssy/continuous_junnan/ssy_wc_ratio_continuous.py:125-226 and

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsdfs_b200.so")
-SOURCES = ["api.cu", "builder.cu", "ops.cu", "loops.cu", "loops_dense.cu", "loops_kron_sa.cu", "loops_kron_newton.cu",
+SOURCES = ["api.cu", "builder.cu", "ops.cu", "kron_apply.cu", "loops.cu", "loops_dense.cu", "loops_kron_sa.cu", "loops_kron_newton.cu",
            "loops_kron_anderson.cu", "loops_cont.cu",
            "comm.cu", "sweep.cu", "small.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

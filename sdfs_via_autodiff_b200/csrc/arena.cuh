@@ -43,3 +43,4 @@ void *comm_peer_arena(sdfs_ctx *ctx, int r);
 int64_t comm_arena_maxN(sdfs_ctx *ctx);
 unsigned long long *comm_epoch(sdfs_ctx *ctx);
 int comm_allgather_rows(sdfs_ctx *ctx, double *d_vec, int64_t N);
+int comm_allgather_parts(sdfs_ctx *ctx, double *d_vec, const int64_t *rb, const int64_t *re);

@@ -274,18 +274,22 @@ fail:
 // ---------------------------------------------------------------------------
 // Mode description shared by the factor-form apply and the dense expansion.
 // ---------------------------------------------------------------------------
+#define KRON_TC_MIN_HOST 9      // = KRON_TC_MIN of rowdot.cuh (shortest axis on the tensor-core contraction)
 int factors_to_kron(const sdfs_factors *f, KronView *kv) {
     memset(kv, 0, sizeof(*kv));
     kv->D = f->D;
     kv->N = 1;
     for (int d = 0; d < f->D; ++d) { kv->shape[d] = f->shapes[d]; kv->N *= f->shapes[d]; }
     if (f->model == SDFS_MODEL_SSY) {
-        // contraction order of the sum-factorised apply: i' (Q_hz), j' (z_Q[i]), k' (Q_c), l' (Q_lam)
+        // contraction order of the sum-factorised apply: l' (Q_lam) first -- the leading axis is the one a
+        // multi-GPU run splits into slabs, and contracting it first is the only step that needs the other
+        // ranks' part of the input, so everything after it is rank-local (the same order on one GPU keeps
+        // results bit-identical across rank counts) -- then i' (Q_hz), j' (z_Q[i], needs the current i), k' (Q_c)
         kv->n_modes = 4;
-        kv->modes[0].mat = f->d_arr[5]; kv->modes[0].dim = 2;
-        kv->modes[1].mat = f->d_arr[7]; kv->modes[1].dim = 3; kv->modes[1].mstride[2] = 1;
-        kv->modes[2].mat = f->d_arr[3]; kv->modes[2].dim = 1;
-        kv->modes[3].mat = f->d_arr[1]; kv->modes[3].dim = 0;
+        kv->modes[0].mat = f->d_arr[1]; kv->modes[0].dim = 0;
+        kv->modes[1].mat = f->d_arr[5]; kv->modes[1].dim = 2;
+        kv->modes[2].mat = f->d_arr[7]; kv->modes[2].dim = 3; kv->modes[2].mstride[2] = 1;
+        kv->modes[3].mat = f->d_arr[3]; kv->modes[3].dim = 1;
     } else {
         const int nhz = f->shapes[2], nhzp = f->shapes[4];
         kv->n_modes = 6;
@@ -317,8 +321,42 @@ int factors_to_kron(const sdfs_factors *f, KronView *kv) {
                 md.Fcount *= kv->shape[d]; md.nF++;
             }
         }
+        md.out0 = 0; md.nout = kv->shape[md.dim]; md.base_off = 0; md.colscale = nullptr;
     }
+    kv->lead0 = 0; kv->leadn = kv->shape[0];
+    kv->row_begin = 0; kv->row_end = kv->N;
     return SDFS_OK;
+}
+
+// Can the leading axis of this view be split into per-rank slabs?  The mode that contracts axis 0 must come
+// first (its matrix cannot depend on another coordinate, and no other matrix may depend on coordinate 0) and
+// run on the tensor-core path, which has the restricted-output variant.  True for SSY (axis 0 = h_lambda);
+// false for GCY, whose leading axis z is contracted last by matrices indexed by (z_pi, h_z, h_zpi).
+bool kron_can_shard(const KronView &kv) {
+    const KronMode &m0 = kv.modes[0];
+    if (m0.dim != 0 || m0.nM != 0) return false;
+    for (int m = 1; m < kv.n_modes; ++m)
+        if (kv.modes[m].mstride[0] != 0) return false;
+    return kv.shape[0] >= KRON_TC_MIN_HOST && kv.shape[0] <= 64;
+}
+
+// Restrict a view to the slab [l0, l1) of axis 0: rows [l0, l1) x (everything else) of the result.
+void kron_restrict_leading(KronView *kv, int l0, int l1) {
+    const long long inner = kv->N / kv->shape[0];
+    kv->lead0 = l0; kv->leadn = l1 - l0;
+    kv->row_begin = (int64_t)l0 * inner; kv->row_end = (int64_t)l1 * inner;
+    KronMode &m0 = kv->modes[0];
+    m0.out0 = l0; m0.nout = l1 - l0;
+    for (int m = 1; m < kv->n_modes; ++m) {
+        KronMode &md = kv->modes[m];
+        md.base_off = (long long)l0 * inner;
+        for (int a = 0; a < md.nF; ++a)
+            if (md.Fstride[a] == inner) {          // axis 0 comes first in the free-axis list and is the slowest axis
+                md.Fcount = md.Fcount / md.Fshape[a] * (l1 - l0);
+                md.Fshape[a] = l1 - l0;
+                break;
+            }
+    }
 }
 
 // a_row, a_col, e_sdf for every state (C-order flattening, temp_ssy.py:41-42).

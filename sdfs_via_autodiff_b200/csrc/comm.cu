@@ -95,24 +95,29 @@ static inline void rank_rows(int64_t N, int nranks, int rank, int64_t *rb, int64
     *rb = b; *re = e;
 }
 
-// In-place all-gather of the per-rank row slices of a full-length vector.
-int comm_allgather_rows(sdfs_ctx *ctx, double *d_vec, int64_t N) {
+// In-place all-gather of a full-length vector: rank r owns rows [rb[r], re[r]) (contiguous, in rank order).
+int comm_allgather_parts(sdfs_ctx *ctx, double *d_vec, const int64_t *rb, const int64_t *re) {
     if (ctx->nranks <= 1) return SDFS_OK;
     if (!ctx->comm || !ctx->comm->comm) return sdfs_set_error(ctx, SDFS_ERR_COMM, "communicator not initialised");
-    const int64_t chunk = (N + ctx->nranks - 1) / ctx->nranks;
-    if (chunk * ctx->nranks == N) {
-        NCCL_TRY(ctx, g_nccl.AllGather(d_vec + chunk * ctx->rank, d_vec, (size_t)chunk, ncclFloat64, ctx->comm->comm, ctx->stream));
+    bool equal = rb[0] == 0;
+    for (int r = 1; r < ctx->nranks; ++r) equal = equal && (re[r] - rb[r] == re[0] - rb[0]) && rb[r] == re[r - 1];
+    if (equal) {
+        NCCL_TRY(ctx, g_nccl.AllGather(d_vec + rb[ctx->rank], d_vec, (size_t)(re[0] - rb[0]), ncclFloat64, ctx->comm->comm, ctx->stream));
     } else {
         NCCL_TRY(ctx, g_nccl.GroupStart());
-        for (int r = 0; r < ctx->nranks; ++r) {
-            int64_t rb, re;
-            rank_rows(N, ctx->nranks, r, &rb, &re);
-            if (re > rb)
-                NCCL_TRY(ctx, g_nccl.Broadcast(d_vec + rb, d_vec + rb, (size_t)(re - rb), ncclFloat64, r, ctx->comm->comm, ctx->stream));
-        }
+        for (int r = 0; r < ctx->nranks; ++r)
+            if (re[r] > rb[r])
+                NCCL_TRY(ctx, g_nccl.Broadcast(d_vec + rb[r], d_vec + rb[r], (size_t)(re[r] - rb[r]), ncclFloat64, r, ctx->comm->comm, ctx->stream));
         NCCL_TRY(ctx, g_nccl.GroupEnd());
     }
     return SDFS_OK;
+}
+
+// ... with the default row partition of a vector of length N
+int comm_allgather_rows(sdfs_ctx *ctx, double *d_vec, int64_t N) {
+    int64_t rb[SDFS_MAX_RANKS], re[SDFS_MAX_RANKS];
+    for (int r = 0; r < ctx->nranks; ++r) rank_rows(N, ctx->nranks, r, &rb[r], &re[r]);
+    return comm_allgather_parts(ctx, d_vec, rb, re);
 }
 
 

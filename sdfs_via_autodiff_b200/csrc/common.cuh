@@ -95,6 +95,14 @@ struct KronMode {
     int Fshape[SDFS_MAX_DIMS], Mshape[SDFS_MAX_DIMS], Mmat[SDFS_MAX_DIMS];
     long long Fstride[SDFS_MAX_DIMS], Mstride[SDFS_MAX_DIMS];
     long long stride, Fcount, Mcount;
+    // slab-sharded views (one process per GPU, leading axis split over the ranks; kron_restrict_leading):
+    // the leading mode forms only the output rows [out0, out0 + nout) of its axis from the full input, the
+    // other modes run on the local slab (axis 0 restricted in Fshape, element offset base_off)
+    int out0, nout;
+    long long base_off;
+    // optional scaling of the matrix columns (next-period index), applied while the matrix is staged: the fused
+    // apply folds a_col (a function of this axis alone) into the first contraction instead of reading an N-vector
+    const double *colscale;
 };
 struct KronView {
     int D;
@@ -104,6 +112,8 @@ struct KronView {
     KronMode modes[SDFS_MAX_DIMS];
     const double *a_row, *a_col, *e_sdf;
     double beta, theta;
+    int lead0, leadn;                  // slab [lead0, lead0 + leadn) of axis 0 owned by this rank (whole axis when not sharded)
+    int64_t row_begin, row_end;        // = lead0 * N / shape[0], (lead0 + leadn) * N / shape[0]
 };
 
 // Continuous-state operator (ssy/continuous_junnan/ssy_wc_ratio_continuous.py,
@@ -137,7 +147,8 @@ struct sdfs_op {
     sdfs_ctx *ctx = nullptr;
     int storage = SDFS_STORAGE_DENSE;
     DenseView dv{};
-    KronView kv{};
+    KronView kv{};                     // whole operator (builder kernels, dense expansion, sweeps)
+    KronView kvs{};                    // what applications and solver loops of THIS rank contract: kv, or its slab-sharded restriction
     ContView cv{};
     double *cont_mem = nullptr;        // grids + nodes + weights of a continuous-state operator
     sdfs_factors *factors = nullptr;   // borrowed (kept alive by the host wrapper)
@@ -151,9 +162,15 @@ struct sdfs_op {
     double *kron_tmp[2] = {nullptr, nullptr};
     double gamma = 0, psi = 0, mu_c = 0;  // remembered for set_preferences
     int sweep_form = 0;                // SDFS_SWEEP_DENSE | SDFS_SWEEP_FACTOR
+    bool kron_sharded = false;         // factor form with the leading axis split into per-rank slabs
+    double *a_col_lead = nullptr;      // a_col along the axis of the first contraction (it is constant along the others)
 };
 
 int op_ensure_work(sdfs_op *op, int n_vectors);
+void op_sync_kvs(sdfs_op *op);                                           // ops.cu
+void op_rank_rows(const sdfs_op *op, int r, int64_t *rb, int64_t *re);   // ops.cu
+bool op_is_sharded(const sdfs_op *op);                                   // ops.cu
+int op_allgather(sdfs_op *op, double *d_vec);                            // ops.cu
 static inline int64_t op_N(const sdfs_op *op) {
     return op->storage == SDFS_STORAGE_DENSE ? op->dv.N : (op->storage == SDFS_STORAGE_KRON ? op->kv.N : op->cv.N);
 }

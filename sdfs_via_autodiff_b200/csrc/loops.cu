@@ -9,9 +9,8 @@ static int build_env(sdfs_op *op, LoopEnv *env) {
     env->nranks = ctx->nranks;
     env->status = (LoopStatus *)ctx->d_status;
     const int64_t N = op_N(op);
-    const bool sharded = ctx->nranks > 1 && op->storage == SDFS_STORAGE_DENSE &&
-                         (op->dv.row_end - op->dv.row_begin) < op->dv.N;
-    if (!sharded) {   // single GPU, factor form, or a replicated dense operator: purely local loop
+    const bool sharded = op_is_sharded(op);     // row-sharded dense P or slab-sharded factor form
+    if (!sharded) {   // single GPU, or an operator that is whole on this rank: purely local loop
         env->rank = 0;
         env->nranks = 1;
         if (!op->slots) {
@@ -98,7 +97,7 @@ int sdfs_solve_sa(sdfs_op *op, const double *d_w_init, double tol, int64_t max_i
     TRY(finish_loop(ctx, hs, 0));
     if (env.nranks > 1) {
         *comm_epoch(ctx) = hs->epoch_end;   // every rank passed the same barriers
-        TRY(comm_allgather_rows(ctx, d_w_out, op_N(op)));
+        TRY(op_allgather(op, d_w_out));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (iters) *iters = hs->iters;
@@ -135,7 +134,7 @@ int sdfs_solve_anderson(sdfs_op *op, const double *d_w_init, double tol, int64_t
     TRY(finish_loop(ctx, hs, 0));
     if (env.nranks > 1) {
         *comm_epoch(ctx) = hs->epoch_end;
-        TRY(comm_allgather_rows(ctx, d_w_out, N));
+        TRY(op_allgather(op, d_w_out));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (iters) *iters = hs->iters;
@@ -180,7 +179,7 @@ int sdfs_solve_newton(sdfs_op *op, const double *d_w_init, double tol, int64_t m
     TRY(finish_loop(ctx, hs, 0));
     if (env.nranks > 1) {
         *comm_epoch(ctx) = hs->epoch_end;   // every rank passed the same barriers
-        TRY(comm_allgather_rows(ctx, d_w_out, N));
+        TRY(op_allgather(op, d_w_out));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if (outer_iters) *outer_iters = hs->iters;

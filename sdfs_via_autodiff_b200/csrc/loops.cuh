@@ -30,6 +30,7 @@ int small_sa_try(sdfs_op *op, const double *d_w_init, double tol, int64_t max_it
 
 #define HIST_CAP 120       // outer Newton iterations recorded in the status page
 #define GMRES_MAX_RESTART 64
+#define GMRES_WS_BYTES (((GMRES_MAX_RESTART + 1) * 2 + GMRES_MAX_RESTART * 3 + GMRES_MAX_RESTART * GMRES_MAX_RESTART) * sizeof(double) + 16)
 
 struct LoopStatus {        // lives in ctx->d_status (4 KB)
     long long iters;
@@ -182,6 +183,7 @@ struct Scratch {
     RowPipe<1> *rp;        // TMA ring in dynamic shared memory (dense operators)
     PipeState st;
     double *smat;          // factor matrix staging (factor-form operators), dynamic shared memory
+    double *stage;         // per-warp fragment stage of the tensor-core contraction (rowdot.cuh), after smat
 };
 
 struct DenseLoopOp {
@@ -224,11 +226,11 @@ struct KronLoopOp {
     static constexpr int kMinBlocks = 2;     // <= 112 registers: two 288-thread CTAs (18 warps) per SM hide the fragment-load latency
     KronView kv;
     double *tmp0, *tmp1;
-    __host__ __device__ size_t dyn_smem() const { return KRON_SMAT_DOUBLES * sizeof(double); }
+    __host__ __device__ size_t dyn_smem() const { return (KRON_SMAT_DOUBLES + SDFS_WARPS * KRON_STAGE_DOUBLES_PER_WARP) * sizeof(double); }
     __device__ __forceinline__ void init(Scratch &) const {}
     __device__ __forceinline__ int64_t N() const { return kv.N; }
-    __device__ __forceinline__ int64_t row_begin() const { return 0; }
-    __device__ __forceinline__ int64_t row_end() const { return kv.N; }
+    __device__ __forceinline__ int64_t row_begin() const { return kv.row_begin; }     // slab of the leading axis (sharded view)
+    __device__ __forceinline__ int64_t row_end() const { return kv.row_end; }
     __device__ __forceinline__ const double *a_row() const { return kv.a_row; }
     __device__ __forceinline__ const double *a_col() const { return kv.a_col; }
     __device__ __forceinline__ double beta() const { return kv.beta; }
@@ -248,11 +250,11 @@ struct KronLoopOp {
         const double *in = xin;
         for (int m = 0; m < kv.n_modes - 1; ++m) {
             double *out = (m & 1) ? tmp1 : tmp0;
-            kron_mode_store(kv, m, in, out, sc.smat);
+            kron_mode_store(kv, m, in, out, sc.smat, sc.stage);
             if (!all_sync(grid, env, epoch)) return false;
             in = out;
         }
-        kron_mode_apply(kv, kv.n_modes - 1, in, sc.smat, [&](int64_t idx, double s) { epi(idx, s); });
+        kron_mode_apply(kv, kv.n_modes - 1, in, sc.smat, [&](int64_t idx, double s) { epi(idx, s); }, KronShare(sc.stage));
         return true;
     }
 };
@@ -308,6 +310,7 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_sa_loop(const 
     Scratch sc;
     sc.rp = reinterpret_cast<RowPipe<1> *>(dyn_smem);
     sc.smat = reinterpret_cast<double *>(dyn_smem);
+    sc.stage = sc.smat + KRON_SMAT_DOUBLES;
     op.init(sc);
     unsigned long long epoch = env.epoch0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -613,8 +616,11 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_newton_loop(co
     Scratch sc;
     sc.rp = reinterpret_cast<RowPipe<1> *>(dyn_smem);
     sc.smat = reinterpret_cast<double *>(dyn_smem);
+    sc.stage = sc.smat + KRON_SMAT_DOUBLES;
     op.init(sc);
-    __shared__ double hs[(GMRES_MAX_RESTART + 1) * 2 + GMRES_MAX_RESTART * 3 + GMRES_MAX_RESTART * GMRES_MAX_RESTART];
+    // GMRES Hessenberg workspace: dynamic shared memory behind the operator's region, present only when the
+    // host selected GMRES (35 KB that would otherwise cost the factor-form loops their second CTA per SM)
+    double *hs = reinterpret_cast<double *>(dyn_smem + ((op.dyn_smem() + 15) & ~(size_t)15));
     unsigned long long epoch = env.epoch0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nth = (int64_t)gridDim.x * blockDim.x;
@@ -743,6 +749,7 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_anderson_loop(
     Scratch sc;
     sc.rp = reinterpret_cast<RowPipe<1> *>(dyn_smem);
     sc.smat = reinterpret_cast<double *>(dyn_smem);
+    sc.stage = sc.smat + KRON_SMAT_DOUBLES;
     op.init(sc);
     unsigned long long epoch = env.epoch0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -861,6 +868,9 @@ static int loop_launch(sdfs_ctx *ctx, Op &lop, void *a, LoopEnv *env, size_t dyn
     if constexpr (WHICH == LOOP_SA) kern = (const void *)k_sa_loop<Op>;
     else if constexpr (WHICH == LOOP_NEWTON) kern = (const void *)k_newton_loop<Op>;
     else kern = (const void *)k_anderson_loop<Op>;
+    if constexpr (WHICH == LOOP_NEWTON) {      // GMRES Hessenberg workspace behind the operator's region
+        if (((const NewtonArgs *)a)->krylov == SDFS_KRYLOV_GMRES) dyn_smem = ((dyn_smem + 15) & ~(size_t)15) + GMRES_WS_BYTES;
+    }
     int grid = 0;
     TRY(coop_grid(ctx, kern, dyn_smem, max_per_sm, work_groups, force_full, &grid));
     void *args[] = {&lop, a, env};

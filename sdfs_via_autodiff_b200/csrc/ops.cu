@@ -3,8 +3,12 @@
 #include "rowdot.cuh"
 #include "arena.cuh"
 #include "cont.cuh"
+#include "epilogue.cuh"
+#include "kron_apply.cuh"
 
 int factors_to_kron(const sdfs_factors *f, KronView *kv);
+bool kron_can_shard(const KronView &kv);
+void kron_restrict_leading(KronView *kv, int l0, int l1);
 int launch_build_scalings(sdfs_ctx *ctx, const sdfs_factors *f, const KronView &kv, double gamma,
                           double theta, double mu_c, double *a_row, double *a_col, double *e_sdf);
 int launch_expand_dense(sdfs_ctx *ctx, const KronView &kv, int64_t row_begin, int64_t row_end, int64_t ld, double *P);
@@ -44,86 +48,6 @@ __global__ void k_prologue(int mode, int64_t N, const double *__restrict__ a_col
     }
 }
 
-// Epilogue modes of the dense / factor-form pass
-//  0: out0 = 1 + beta (a_row s0)^(1/theta)                                   (T)
-//  1: out0 = beta (a_row s0)^((1-theta)/theta) a_row s1                      (J_T(w) v)
-//  2: out0 = beta^theta e_sdf (w-1)^(1-theta) s1 ; out1 = beta^theta a_row s0/(w-1)^theta - 1 (SDF)
-//  3: out0 = s0                                                              (P x)
-struct EpiArgs {
-    int mode;
-    const double *a_row, *e_sdf, *w;
-    double beta, theta;
-    double *out0, *out1;
-    double inv_theta = 0.0;     // 1 / theta, filled by the launchers
-};
-
-template <bool FAST = false>
-__device__ __forceinline__ void apply_epilogue(const EpiArgs &e, int64_t n, double s0, double s1) {
-    auto pw = [](double x, double ex) { return FAST ? pow_pos(x, ex) : pow(x, ex); };
-    if (e.mode == 0) {
-        e.out0[n] = 1.0 + e.beta * pw(e.a_row[n] * s0, e.inv_theta);
-    } else if (e.mode == 1) {
-        const double ar = e.a_row[n];
-        e.out0[n] = e.beta * pw(ar * s0, e.inv_theta - 1.0) * ar * s1;
-    } else if (e.mode == 2) {
-        const double bt = pow(e.beta, e.theta);
-        const double wm1 = e.w[n] - 1.0;
-        if (e.out0) e.out0[n] = bt * e.e_sdf[n] * pw(wm1, 1.0 - e.theta) * s1;
-        if (e.out1) e.out1[n] = bt * (e.a_row[n] * s0) / pw(wm1, e.theta) - 1.0;
-    } else {
-        e.out0[n] = s0;
-    }
-}
-
-// single-output epilogues (T, JVP, plain P x) as a value, for the fused exchange below
-__device__ __forceinline__ double epilogue_value(const EpiArgs &e, int64_t n, double s0, double s1) {
-    if (e.mode == 0) return 1.0 + e.beta * pow(e.a_row[n] * s0, e.inv_theta);
-    if (e.mode == 1) {
-        const double ar = e.a_row[n];
-        return e.beta * pow(ar * s0, e.inv_theta - 1.0) * ar * s1;
-    }
-    return s0;
-}
-
-// Fused exchange of a row-sharded single application (one process per GPU): the epilogue stores its
-// rows straight into the result buffer of EVERY rank (NVLink peer stores into the CUDA-IPC arenas),
-// and the last CTA of the kernel to finish trades an epoch flag with the peers, so when the kernel
-// ends the full vector is in this rank's arena - no collective launch follows the row pass.
-struct PeerArgs {
-    int nranks, rank;                          // nranks <= 1: plain local stores through EpiArgs
-    double *out[SDFS_MAX_RANKS];               // result buffer y[epoch & 1] in rank r's arena
-    unsigned long long *sig[SDFS_MAX_RANKS];   // rank r's flag word for this rank
-    unsigned long long *mine;                  // this rank's flag words (written by the peers)
-    unsigned long long epoch;
-    unsigned int *counter;                     // CTAs of this launch that have finished (self-resetting)
-    long long *h_abort;                        // pinned host word: set when a peer never arrives
-};
-
-__device__ __forceinline__ void peer_exchange_finish(const PeerArgs &pa) {
-    __syncthreads();                           // every store of this CTA issued
-    if (threadIdx.x == 0) {
-        __threadfence_system();                // ... and ordered before the arrival count
-        const unsigned int done = atomicAdd(pa.counter, 1u);
-        if (done == gridDim.x - 1) {           // last CTA of this rank
-            *pa.counter = 0;
-            __threadfence_system();
-            for (int r = 0; r < pa.nranks; ++r)
-                if (r != pa.rank) st_release_sys(pa.sig[r], pa.epoch);
-            const long long t0 = clock64();
-            for (int r = 0; r < pa.nranks; ++r) {
-                if (r == pa.rank) continue;
-                while (ld_acquire_sys(pa.mine + r) < pa.epoch) {
-                    if (clock64() - t0 > SDFS_PEER_TIMEOUT_CLOCKS) {
-                        *(volatile long long *)pa.h_abort = 1;
-                        __threadfence_system();
-                        return;
-                    }
-                }
-            }
-        }
-    }
-}
-
 // elementwise epilogue at full occupancy (factor-form path: the contraction kernels run at 8-12
 // warps per SM, far too few to hide the latency of one pow per output)
 __global__ void k_epilogue_ew(int64_t N, const double *__restrict__ s0, const double *__restrict__ s1, EpiArgs e) {
@@ -160,9 +84,10 @@ k_dense_apply(const __grid_constant__ DenseView dv, const double *x0, const doub
 }
 
 __global__ void __launch_bounds__(256) k_kron_mode(KronView kv, int m, const double *__restrict__ in, double *__restrict__ out) {
-    __shared__ __align__(16) double smat[KRON_SMAT_DOUBLES];
-    kron_mode_apply<true>(kv, m, in, smat, [&](int64_t idx, double s) { out[idx] = s; });
+    extern __shared__ __align__(16) double kron_smem[];      // factor matrix + per-warp fragment stage
+    kron_mode_apply<true>(kv, m, in, kron_smem, KronSinkStore{out}, KronShare(kron_smem + KRON_SMAT_DOUBLES));
 }
+
 // 2-D TMA descriptor of the local row slice of P: dims (N columns, nloc rows), row pitch ld,
 // box 256 columns x 8 rows, zero fill outside the matrix.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -193,6 +118,66 @@ int dense_view_finalize(sdfs_ctx *ctx, DenseView *dv) {
         memset(&dv->tm, 0, sizeof(dv->tm));
     }
     return SDFS_OK;
+}
+
+// a_col along the axis of the first contraction (other coordinates 0)
+__global__ void k_gather_strided(int n, long long stride, const double *__restrict__ src, double *__restrict__ dst) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) dst[j] = src[(long long)j * stride];
+}
+static int op_refresh_a_col_lead(sdfs_op *op) {
+    sdfs_ctx *ctx = op->ctx;
+    const KronMode &m0 = op->kv.modes[0];
+    const int n = op->kv.shape[m0.dim];
+    if (!op->a_col_lead) CUDA_TRY(ctx, cudaMalloc(&op->a_col_lead, (size_t)n * sizeof(double)));
+    k_gather_strided<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, m0.stride, op->own_a_col, op->a_col_lead);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SDFS_OK;
+}
+
+// leading-axis slab of rank r: ceil(L / ranks) indices each, the last ranks possibly fewer or none
+static inline void kron_slab(int L, int nranks, int r, int *l0, int *l1) {
+    const int chunk = (L + nranks - 1) / nranks;
+    int b = chunk * r, e = b + chunk;
+    if (b > L) b = L;
+    if (e > L) e = L;
+    *l0 = b; *l1 = e;
+}
+
+// kvs = what this rank contracts: the whole view, or its slab restriction (call after every change of kv)
+void op_sync_kvs(sdfs_op *op) {
+    op->kvs = op->kv;
+    if (op->kron_sharded) {
+        int l0, l1;
+        kron_slab(op->kv.shape[0], op->ctx->nranks, op->ctx->rank, &l0, &l1);
+        kron_restrict_leading(&op->kvs, l0, l1);
+    }
+}
+
+// rows of the result that rank r computes (dense row shards, factor-form slabs, or everything)
+void op_rank_rows(const sdfs_op *op, int r, int64_t *rb, int64_t *re) {
+    const int64_t N = op_N(op);
+    const int G = op->ctx->nranks;
+    if (op->storage == SDFS_STORAGE_KRON && op->kron_sharded) {
+        int l0, l1;
+        kron_slab(op->kv.shape[0], G, r, &l0, &l1);
+        const int64_t inner = N / op->kv.shape[0];
+        *rb = l0 * inner; *re = l1 * inner;
+    } else if (op->storage == SDFS_STORAGE_DENSE && G > 1 && op->dv.row_end - op->dv.row_begin < N) {
+        const int64_t chunk = (N + G - 1) / G;
+        int64_t b = chunk * r, e = b + chunk;
+        if (b > N) b = N;
+        if (e > N) e = N;
+        *rb = b; *re = e;
+    } else {
+        *rb = 0; *re = N;
+    }
+}
+bool op_is_sharded(const sdfs_op *op) {
+    int64_t rb, re;
+    op_rank_rows(op, op->ctx->rank, &rb, &re);
+    return op->ctx->nranks > 1 && re - rb < op_N(op);
 }
 
 int op_ensure_work(sdfs_op *op, int n_vectors) {
@@ -325,11 +310,25 @@ int launch_kron_mode(sdfs_ctx *ctx, const KronView &kv, int m, const double *in,
     const bool tc = nm >= KRON_TC_MIN && nm <= KRON_NMAX_LIMIT;
     const int threads = tc ? kron_tc_threads : (fibres >= (long long)ctx->sm_count * 128 ? 128 : 64);
     const int grid = tc ? ctx->sm_count * kron_tc_ctas : ctx->sm_count * 6;
-    k_kron_mode<<<grid, threads, 0, ctx->stream>>>(kv, m, in, out);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_kron_mode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KRON_APPLY_SMEM));
+        attr_set = true;
+    }
+    k_kron_mode<<<grid, threads, KRON_APPLY_SMEM, ctx->stream>>>(kv, m, in, out);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return SDFS_OK;
 }
+
+// In-place all-gather of a full-length vector whose rows were computed by their owning ranks
+int op_allgather(sdfs_op *op, double *d_vec) {
+    int64_t rb[SDFS_MAX_RANKS], re[SDFS_MAX_RANKS];
+    for (int r = 0; r < op->ctx->nranks; ++r) op_rank_rows(op, r, &rb[r], &re[r]);
+    return comm_allgather_parts(op->ctx, d_vec, rb, re);
+}
+
+int launch_kron_apply(sdfs_ctx *ctx, const KronView &kv, const KronApplyArgs &ka, const EpiArgs &e, const PeerArgs &pa);   // kron_apply.cu
 
 // Shared driver: prologue -> P pass(es) -> epilogue.
 static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_v, EpiArgs e, bool gather0,
@@ -344,10 +343,9 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
     const int nx = (pmode == 1 || pmode == 2) ? 2 : 1;
     const double *a_col = dense ? op->dv.a_col : op->kv.a_col;
     const double theta = dense ? op->dv.theta : op->kv.theta;
-    if (dense) k_prologue<false><<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(pmode, N, a_col, d_w, d_v, theta, x0, x1);
-    else k_prologue<true><<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(pmode, N, a_col, d_w, d_v, theta, x0, x1);
-    ctx->launches++;
     if (dense) {
+        k_prologue<false><<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(pmode, N, a_col, d_w, d_v, theta, x0, x1);
+        ctx->launches++;
         const bool sharded = ctx->nranks > 1 && op->dv.row_end - op->dv.row_begin < N;
         PeerArgs pa;
         memset(&pa, 0, sizeof(pa));
@@ -378,28 +376,47 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
         if (fused) {
             CUDA_TRY(ctx, cudaMemcpyAsync(e.out0, pa.out[ctx->rank], (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         } else if (sharded) {
-            if (gather0 && e.out0) TRY(comm_allgather_rows(ctx, e.out0, N));
-            if (gather1 && e.out1) TRY(comm_allgather_rows(ctx, e.out1, N));
+            if (gather0 && e.out0) TRY(op_allgather(op, e.out0));
+            if (gather1 && e.out1) TRY(op_allgather(op, e.out1));
         }
     } else {
-        const KronView &kv = op->kv;
+        const KronView &kv = op->kvs;
         if (!op->kron_tmp[0]) {
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[0], (size_t)N * sizeof(double)));
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)N * sizeof(double)));
         }
-        // work items of the fibre kernel are distributed round-robin: any grid size is valid
-        double *sfin[2] = {op->work + 2 * op->ldv, op->work + 3 * op->ldv};     // finished contractions
-        for (int pass = 0; pass < nx; ++pass) {
-            const double *in = (pass == 0) ? x0 : x1;
-            for (int m = 0; m < kv.n_modes; ++m) {
-                double *out = (m == kv.n_modes - 1) ? sfin[pass] : op->kron_tmp[m & 1];
-                TRY(launch_kron_mode(ctx, kv, m, in, out));
-                in = out;
+        KronApplyArgs ka{};
+        ka.pmode = pmode; ka.w = d_w; ka.v = d_v;
+        ka.tmp0 = op->kron_tmp[0]; ka.tmp1 = op->kron_tmp[1];
+        ka.s0 = op->work + 2 * op->ldv;
+        const bool sharded = op->kron_sharded;
+        PeerArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        static const bool fused_allowed = !(getenv("SDFS_FUSED_EXCHANGE") && atoi(getenv("SDFS_FUSED_EXCHANGE")) == 0);
+        const bool fused = sharded && fused_allowed && e.mode != 2 && gather0 && e.out0 && comm_peers_ready(ctx) &&
+                           comm_arena_maxN(ctx) >= N;
+        if (fused) {
+            unsigned long long *ep = comm_epoch(ctx);
+            *ep += 1;
+            pa.nranks = ctx->nranks; pa.rank = ctx->rank; pa.epoch = *ep;
+            for (int r = 0; r < ctx->nranks; ++r) {
+                void *base = comm_peer_arena(ctx, r);
+                pa.out[r] = arena_apply_buf(base, comm_arena_maxN(ctx), (int)(*ep & 1));
+                pa.sig[r] = (unsigned long long *)base + ctx->rank;
             }
+            pa.mine = (unsigned long long *)comm_peer_arena(ctx, ctx->rank);
+            pa.counter = (unsigned int *)((char *)ctx->d_status + 4096 - 64);
+            pa.h_abort = ctx_h_abort(ctx);
         }
-        k_epilogue_ew<<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(N, sfin[0], nx > 1 ? sfin[1] : nullptr, e);
-        ctx->launches++;
-        CUDA_TRY(ctx, cudaGetLastError());
+        KronView kvl = kv;                                      // launch copy: a_col rides in the first factor matrix
+        if (pmode != 3) kvl.modes[0].colscale = op->a_col_lead;
+        TRY(launch_kron_apply(ctx, kvl, ka, e, pa));
+        if (fused) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(e.out0, pa.out[ctx->rank], (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        } else if (sharded) {
+            if (gather0 && e.out0) TRY(op_allgather(op, e.out0));
+            if (gather1 && e.out1) TRY(op_allgather(op, e.out1));
+        }
     }
     return SDFS_OK;
 }
@@ -429,9 +446,12 @@ int sdfs_op_from_dense(sdfs_ctx *ctx, const double *d_P, int64_t N, int64_t ld, 
 
 int sdfs_op_from_factors(sdfs_ctx *ctx, sdfs_factors *f, int storage, sdfs_op **out) {
     ARG_CHECK(ctx, ctx && f && out && f->ctx == ctx);
-    ARG_CHECK(ctx, storage == SDFS_STORAGE_DENSE || storage == SDFS_STORAGE_KRON || storage == SDFS_STORAGE_DENSE_REPLICATED);
+    ARG_CHECK(ctx, storage == SDFS_STORAGE_DENSE || storage == SDFS_STORAGE_KRON || storage == SDFS_STORAGE_DENSE_REPLICATED ||
+                   storage == SDFS_STORAGE_KRON_LOCAL);
     const bool replicated = storage == SDFS_STORAGE_DENSE_REPLICATED;
     if (replicated) storage = SDFS_STORAGE_DENSE;
+    const bool kron_local = storage == SDFS_STORAGE_KRON_LOCAL;
+    if (kron_local) storage = SDFS_STORAGE_KRON;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     sdfs_op *op = new sdfs_op();
     op->ctx = ctx;
@@ -457,6 +477,13 @@ int sdfs_op_from_factors(sdfs_ctx *ctx, sdfs_factors *f, int storage, sdfs_op **
     if (rc) { sdfs_op_destroy(op); return rc; }
     op->kv.a_row = op->own_a_row; op->kv.a_col = op->own_a_col; op->kv.e_sdf = op->own_e_sdf;
     op->kv.beta = beta; op->kv.theta = theta;
+    rc = op_refresh_a_col_lead(op);
+    if (rc) { sdfs_op_destroy(op); return rc; }
+    // slab-sharded factor form: leading axis split over the ranks (SDFS_KRON_SHARD=0 keeps every rank whole)
+    static const bool shard_allowed = !(getenv("SDFS_KRON_SHARD") && atoi(getenv("SDFS_KRON_SHARD")) == 0);
+    op->kron_sharded = storage == SDFS_STORAGE_KRON && !kron_local && shard_allowed && ctx->nranks > 1 &&
+                       kron_can_shard(op->kv) && op->kv.shape[0] >= ctx->nranks;
+    op_sync_kvs(op);
     if (storage == SDFS_STORAGE_DENSE) {
         const int64_t ld = round_up(N, 64);
         const int64_t chunk = (N + ctx->nranks - 1) / ctx->nranks;
@@ -560,6 +587,7 @@ int sdfs_op_destroy(sdfs_op *op) {
     if (op->slots) cudaFree(op->slots);
     if (op->kron_tmp[0]) cudaFree(op->kron_tmp[0]);
     if (op->kron_tmp[1]) cudaFree(op->kron_tmp[1]);
+    if (op->a_col_lead) cudaFree(op->a_col_lead);
     delete op;
     return SDFS_OK;
 }
@@ -571,8 +599,11 @@ int sdfs_op_info(sdfs_op *op, int64_t *N, int64_t *ld, int64_t *row_begin, int64
     const bool cont = op->storage == SDFS_STORAGE_CONT;
     if (N) *N = op_N(op);
     if (ld) *ld = dense ? op->dv.ld : 0;
-    if (row_begin) *row_begin = dense ? op->dv.row_begin : 0;
-    if (row_end) *row_end = dense ? op->dv.row_end : op_N(op);
+    int64_t rb = 0, re = op_N(op);
+    if (dense) { rb = op->dv.row_begin; re = op->dv.row_end; }
+    else if (op->storage == SDFS_STORAGE_KRON) { rb = op->kvs.row_begin; re = op->kvs.row_end; }
+    if (row_begin) *row_begin = rb;
+    if (row_end) *row_end = re;
     if (beta) *beta = dense ? op->dv.beta : (cont ? op->cv.beta : op->kv.beta);
     if (theta) *theta = dense ? op->dv.theta : (cont ? op->cv.theta : op->kv.theta);
     if (storage) *storage = op->storage;
@@ -606,9 +637,11 @@ int sdfs_op_set_preferences(sdfs_op *op, double gamma, double psi, double beta) 
     const double theta = (1.0 - gamma) / (1.0 - 1.0 / psi);
     TRY(launch_build_scalings(ctx, op->factors, op->kv, gamma, theta, op->mu_c, op->own_a_row, op->own_a_col,
                               op->own_e_sdf));
+    TRY(op_refresh_a_col_lead(op));
     op->gamma = gamma; op->psi = psi;
     op->kv.beta = beta; op->kv.theta = theta;
     op->dv.beta = beta; op->dv.theta = theta;
+    op_sync_kvs(op);
     return SDFS_OK;
 }
 

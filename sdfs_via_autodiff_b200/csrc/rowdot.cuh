@@ -339,15 +339,44 @@ __device__ __forceinline__ void dense_pass(const DenseView &dv, const double *x0
 //   out[idx] = sum_j M[mat_id(idx)][i_m][j] * in[idx with i_m := j]
 // over a grid-stride range of output elements.  Called once per mode with a grid
 // barrier between calls; the last mode feeds the epilogue instead of storing.
-template <class Sink>
-__device__ __forceinline__ void kron_mode_pass(const KronView &kv, int m, const double *in, int64_t tid,
+// Default element loader of the contractions: the stored value.  The fused apply passes a loader that
+// evaluates the operator's prologue (a_col w^theta ...) on the way in, so the first contraction reads w itself.
+struct KronLoadPlain {
+    const double *in;
+    __device__ __forceinline__ double operator()(long long idx) const { return in[idx]; }
+    __device__ __forceinline__ double raw(long long idx) const { return in[idx]; }
+    __device__ __forceinline__ double xform(long long, double x) const { return x; }
+    __device__ __forceinline__ const double *ptr(long long idx) const { return in + idx; }
+};
+// Hooks of the tensor-core contraction for loaders / sinks that carry transcendental work (the fused
+// prologue and epilogue of the operator).  Evaluating a pow per fragment element inside the fully unrolled
+// fragment code costs ~30 inlined pows per instantiation (20 KB of spills and minutes of ptxas time when it
+// was tried).  Instead the warp parks the fragment values in a private shared-memory stage ([16][32]
+// doubles per warp, an indexable register file: lane-private columns, no synchronisation) and a ROLLED loop
+// transforms them two at a time (two independent log/exp chains) - compact code, few live registers.
+//   loader with xform:  raw(idx) is the memory read (issued early: prefetch), xform(idx, x) the arithmetic
+//   staged sink:        operator()(idx, s) is called from the rolled loop instead of the unrolled tail
+template <class L> struct kron_load_traits { static constexpr bool xform = false; };
+template <class S> struct kron_sink_traits { static constexpr bool staged = false; };
+template <class T> struct kron_bare { typedef T type; };
+template <class T> struct kron_bare<T &> { typedef T type; };
+template <class T> struct kron_bare<const T &> { typedef T type; };
+template <class T> struct kron_bare<T &&> { typedef T type; };
+template <class T> struct kron_bare<const T> { typedef T type; };
+
+template <class Load, class Sink>
+__device__ __forceinline__ void kron_mode_pass(const KronView &kv, int m, Load &&load, int64_t tid,
                                                int64_t nthreads, Sink &&sink) {
     const KronMode &md = kv.modes[m];
     const int dim = md.dim;
     const int n = kv.shape[dim];
-    int64_t stride = 1;
-    for (int d = kv.D - 1; d > dim; --d) stride *= kv.shape[d];
-    for (int64_t idx = tid; idx < kv.N; idx += nthreads) {
+    const int64_t stride = md.stride;
+    // output elements of this rank: every axis in full except the slab axis (axis 0), which a sharded view
+    // restricts to [lead0, lead0 + leadn) (as output rows of the leading mode, as a free axis of the others)
+    const int64_t inner = kv.N / kv.shape[0];
+    const int64_t n_out = (int64_t)kv.leadn * inner, off = (int64_t)kv.lead0 * inner;
+    for (int64_t e = tid; e < n_out; e += nthreads) {
+        const int64_t idx = e + off;
         int64_t rem = idx;
         int mat = 0, im = 0;
         for (int d = kv.D - 1; d >= 0; --d) {
@@ -357,9 +386,10 @@ __device__ __forceinline__ void kron_mode_pass(const KronView &kv, int m, const 
             if (d == dim) im = cd;
         }
         const double *row = md.mat + ((int64_t)mat * n + im) * n;
-        const double *src = in + (idx - (int64_t)im * stride);
+        const int64_t src = idx - (int64_t)im * stride;
         double acc = 0.0;
-        for (int j = 0; j < n; ++j) acc = fma(row[j], src[(int64_t)j * stride], acc);
+        if (md.colscale) for (int j = 0; j < n; ++j) acc = fma(row[j] * md.colscale[j], load(src + (int64_t)j * stride), acc);
+        else for (int j = 0; j < n; ++j) acc = fma(row[j], load(src + (int64_t)j * stride), acc);
         sink(idx, acc);
     }
 }
@@ -380,13 +410,15 @@ __device__ __forceinline__ void kron_mode_pass(const KronView &kv, int m, const 
 // contracts a whole (shared-memory resident) vector by itself (fused sweep kernel).
 struct KronShare {
     unsigned cta, nctas;
-    __device__ __forceinline__ KronShare() : cta(blockIdx.x), nctas(gridDim.x) {}
-    __device__ __forceinline__ KronShare(unsigned c, unsigned n) : cta(c), nctas(n) {}
+    double *stage;       // per-CTA staging area (KRON_STAGE_DOUBLES_PER_WARP per warp) when the loader / sink uses it
+    __device__ __forceinline__ KronShare() : cta(blockIdx.x), nctas(gridDim.x), stage(nullptr) {}
+    __device__ __forceinline__ KronShare(unsigned c, unsigned n) : cta(c), nctas(n), stage(nullptr) {}
+    __device__ __forceinline__ explicit KronShare(double *st) : cta(blockIdx.x), nctas(gridDim.x), stage(st) {}
 };
 #define KRON_TC_MIN 9        // shortest axis contracted on the tensor cores (two 8-row output tiles);
                              // kron_mode_fibre<8> serves everything below, so this must stay <= 9
-template <int NMAX, class Sink>
-__device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const double *in, double *smat /* n*NMAX */,
+template <int NMAX, class Load, class Sink>
+__device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, Load &&load, double *smat /* n*NMAX */,
                                                 Sink &&sink, KronShare share = KronShare()) {
     const KronMode &md = kv.modes[m];
     const int n = kv.shape[md.dim];
@@ -395,7 +427,7 @@ __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const
     for (long long item = share.cta; item < items; item += share.nctas) {
         const long long mc = item / chunks, chunk = item - mc * chunks;
         // matrix axes -> matrix id and base offset
-        long long rem = mc, mbase = 0;
+        long long rem = mc, mbase = md.base_off;
         int mat = 0;
         for (int a = md.nM - 1; a >= 0; --a) {
             const int c = (int)(rem % md.Mshape[a]);
@@ -408,7 +440,7 @@ __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const
         const int n4 = (n + 3) & ~3;            // rows padded to a multiple of 4 (zero rows)
         for (int e = threadIdx.x; e < n4 * NMAX; e += blockDim.x) {
             const int i = e / NMAX, j = e - i * NMAX;
-            smat[e] = (i < n && j < n) ? msrc[i * n + j] : 0.0;
+            smat[e] = (i < n && j < n) ? (md.colscale ? msrc[i * n + j] * md.colscale[j] : msrc[i * n + j]) : 0.0;
         }
         __syncthreads();
         const long long f = chunk * blockDim.x + threadIdx.x;
@@ -421,7 +453,7 @@ __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const
             }
             double x[NMAX];
 #pragma unroll
-            for (int j = 0; j < NMAX; ++j) x[j] = (j < n) ? in[base + j * md.stride] : 0.0;
+            for (int j = 0; j < NMAX; ++j) x[j] = (j < n) ? load(base + j * md.stride) : 0.0;
             // four output rows at a time: eight independent FMA chains hide the fp64 latency
             for (int i = 0; i < n; i += 4) {
                 const double2 *r0 = reinterpret_cast<const double2 *>(smat + i * NMAX);
@@ -461,8 +493,173 @@ __device__ __forceinline__ void kron_mode_fibre(const KronView &kv, int m, const
 // range the warps take tiles round-robin and prefetch the next tile's fragments before the DMMAs
 // of the current one.
 // ---------------------------------------------------------------------------
+// RECT: the output rows are the sub-range [out0, out0 + nout) of the contracted axis (the leading mode of a
+// slab-sharded view: this rank forms only its own rows from the full input); IT covers nout, the k steps
+// cover n (up to 64, predicated).
+//
+// Fragment traffic: the A fragments of the NEXT tile are fetched with cp.async (LDGSTS, 8 bytes per lane and
+// k step) straight into a per-warp shared-memory stage ([2][16][32] doubles, lane-private columns: no
+// synchronisation beyond cp.async.wait_group) while the current tile's DMMAs run, and are read back one LDS
+// per k step.  The prefetch therefore costs no registers: the kernel keeps only the 2 IT accumulators live
+// (the register-prefetching version needed 4 IT + 2 IT doubles and ran into the 128-register wall of two
+// CTAs per SM), and the same stage carries the loader / sink hooks above.
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;                            // 0: nothing is read, the 8 bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gsrc), "r"(sz) : "memory");
+}
+#define KRON_STAGE_DOUBLES_PER_WARP (2 * 16 * 32)
+template <int IT /* 8-row output tiles */, bool EXACT /* n > 8 (IT - 1): straight-line k loop */, bool RECT, class Load, class Sink>
+__device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &&load, double *smat, Sink &&sink,
+                                               KronShare share = KronShare()) {
+    constexpr int KT = RECT ? 16 : 2 * IT;                  // n <= 8 IT  =>  ceil(n/4) <= 2 IT
+    constexpr int PITCH = 4 * KT + 4;
+    const KronMode &md = kv.modes[m];
+    const int n = kv.shape[md.dim];
+    const int nout = RECT ? md.nout : n, out0 = RECT ? md.out0 : 0;
+    const int kt_n = (n + 3) >> 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    typedef typename kron_bare<Load>::type LoadT;
+    typedef typename kron_bare<Sink>::type SinkT;
+    constexpr bool XFORM = kron_load_traits<LoadT>::xform, STAGED = kron_sink_traits<SinkT>::staged;
+    double *stw = share.stage + warp * KRON_STAGE_DOUBLES_PER_WARP + lane;     // [buf][kt][lane]
+    const long long tpm = (md.Fcount + 7) >> 3;              // fibre tiles per matrix combination
+    const long long T = md.Mcount * tpm;
+    const long long t_begin = T * share.cta / share.nctas, t_end = T * (share.cta + 1) / share.nctas;
+    const long long kstride = md.stride;
+    const bool small_f = md.Fcount < (1LL << 31);            // 32-bit index decode (always, in practice)
+    int cur_mat = -1;
+    for (long long seg = t_begin; seg < t_end;) {
+        const long long mc = seg / tpm;
+        const long long seg_end = (mc + 1) * tpm < t_end ? (mc + 1) * tpm : t_end;
+        long long rem = mc, mbase = md.base_off;
+        int mat = 0;
+        for (int a = md.nM - 1; a >= 0; --a) {
+            const int c = (int)(rem % md.Mshape[a]);
+            rem /= md.Mshape[a];
+            mat += c * md.Mmat[a];
+            mbase += c * md.Mstride[a];
+        }
+        if (mat != cur_mat) {                   // uniform over the CTA
+            __syncthreads();                    // previous matrix no longer in use
+            const double *msrc = md.mat + (long long)mat * n * n + (long long)out0 * n;
+            for (int e = threadIdx.x; e < IT * 8 * PITCH; e += blockDim.x) {
+                const int i = e / PITCH, j = e - i * PITCH;
+                smat[e] = (i < nout && j < n) ? (md.colscale ? msrc[i * n + j] * md.colscale[j] : msrc[i * n + j]) : 0.0;
+            }
+            __syncthreads();
+            cur_mat = mat;
+        }
+        // fragment fetch: lane (g, q) copies fibre 8 t + g at k = 4 kt + q into stage buffer `buf`
+        auto fetch_tile = [&](long long t, int buf, long long &base, bool &fv) {
+            const long long f = (t - mc * tpm) * 8 + g;
+            fv = f < md.Fcount;
+            base = mbase;
+            if (small_f) {
+                unsigned r2 = fv ? (unsigned)f : 0u;
+                for (int ax = md.nF - 1; ax >= 0; --ax) {
+                    const unsigned sh = (unsigned)md.Fshape[ax], qd = r2 / sh;
+                    base += (long long)(r2 - qd * sh) * md.Fstride[ax];
+                    r2 = qd;
+                }
+            } else {
+                long long r2 = fv ? f : 0;
+                for (int ax = md.nF - 1; ax >= 0; --ax) {
+                    const int c = (int)(r2 % md.Fshape[ax]);
+                    r2 /= md.Fshape[ax];
+                    base += c * md.Fstride[ax];
+                }
+            }
+            const double *p = load.ptr(base + q * kstride);
+            double *dst = stw + buf * (16 * 32);
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                if (EXACT && !RECT ? (kt < KT - 1 || kt < kt_n) : kt < kt_n)
+                    cp_async8(dst + kt * 32, p, fv && kt * 4 + q < n);
+                p += 4 * kstride;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        long long t = seg + warp;
+        long long base = 0, bn = 0;
+        bool fv = false, vn = false;
+        int buf = 0;
+        if (t < seg_end) fetch_tile(t, 0, base, fv);
+        const double *brow = smat + g * PITCH + q;
+        while (t < seg_end) {
+            const long long tn = t + nwarps;
+            if (tn < seg_end) {
+                fetch_tile(tn, buf ^ 1, bn, vn);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            double *st = stw + buf * (16 * 32);
+            if constexpr (XFORM) {              // loader arithmetic in place, rolled: two independent chains per trip
+                if (fv && load.active()) {
+#pragma unroll 1
+                    for (int kt = 0; kt < kt_n; kt += 2) {
+                        const long long p0 = base + (long long)(4 * kt + q) * kstride, p1 = p0 + 4 * kstride;
+                        const bool v0 = 4 * kt + q < n, v1 = kt + 1 < kt_n && 4 * kt + 4 + q < n;
+                        double x0 = st[kt * 32], x1 = v1 ? st[(kt + 1) * 32] : 0.0;
+                        if (v1) { x0 = load.xform(p0, x0); x1 = load.xform(p1, x1); st[(kt + 1) * 32] = x1; }
+                        else if (v0) x0 = load.xform(p0, x0);
+                        st[kt * 32] = x0;
+                    }
+                }
+            }
+            double c[IT][2];
+#pragma unroll
+            for (int it = 0; it < IT; ++it) c[it][0] = c[it][1] = 0.0;
+            // n > 8 (IT - 1) for the exact instantiations, so only the last k step can be absent: the others
+            // form one straight-line block; the even-count and restricted-output variants predicate every step
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                if (EXACT && !RECT ? (kt < KT - 1 || kt < kt_n) : kt < kt_n) {
+                    const double a = st[kt * 32];
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) dmma884(c[it][0], c[it][1], a, brow[it * 8 * PITCH + kt * 4]);
+                }
+            }
+            if constexpr (STAGED) {               // sink arithmetic from the stage, rolled (two outputs per trip)
+#pragma unroll
+                for (int it = 0; it < IT; ++it) { st[(2 * it) * 32] = c[it][0]; st[(2 * it + 1) * 32] = c[it][1]; }
+                if (fv) {
+                    long long idx = base + (out0 + 2 * q) * kstride;
+                    const int it_o = (nout + 7) >> 3;
+#pragma unroll 1
+                    for (int it = 0; it < it_o; ++it) {
+                        const int i = it * 8 + 2 * q;
+                        const double s0 = st[(2 * it) * 32], s1 = st[(2 * it + 1) * 32];
+                        if (i + 1 < nout) sink.pair(idx, idx + kstride, s0, s1);
+                        else if (i < nout) sink(idx, s0);
+                        idx += 8 * kstride;
+                    }
+                }
+            } else if (fv) {
+                long long idx = base + (out0 + 2 * q) * kstride;
+#pragma unroll
+                for (int it = 0; it < IT; ++it) {
+                    const int i = it * 8 + 2 * q;
+                    if (i < nout) sink(idx, c[it][0]);
+                    if (i + 1 < nout) sink(idx + kstride, c[it][1]);
+                    idx += 8 * kstride;
+                }
+            }
+            base = bn; fv = vn;
+            buf ^= 1;
+            t = tn;
+        }
+        seg = seg_end;
+    }
+}
+
+// Register-fed variant of the tensor-core contraction (fragments loaded with plain loads, no stage): for
+// vectors that already live in SHARED memory (the fused sweep kernel contracts a column in place), where
+// cp.async has no global source to copy from and latency is not an issue.
 template <int IT /* 8-row output tiles */, bool PREFETCH, class Sink>
-__device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const double *in, double *smat, Sink &&sink,
+__device__ __forceinline__ void kron_mode_dmma_reg(const KronView &kv, int m, const double *in, double *smat, Sink &&sink,
                                                KronShare share = KronShare()) {
     constexpr int PITCH = 8 * IT + 4, KT = 2 * IT;          // n <= 8 IT  =>  ceil(n/4) <= 2 IT
     const KronMode &md = kv.modes[m];
@@ -479,7 +676,7 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const 
     for (long long seg = t_begin; seg < t_end;) {
         const long long mc = seg / tpm;
         const long long seg_end = (mc + 1) * tpm < t_end ? (mc + 1) * tpm : t_end;
-        long long rem = mc, mbase = 0;
+        long long rem = mc, mbase = md.base_off;
         int mat = 0;
         for (int a = md.nM - 1; a >= 0; --a) {
             const int c = (int)(rem % md.Mshape[a]);
@@ -579,8 +776,8 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, const 
 // latency of its 3-4 fragment loads.  TP tiles per warp iteration, all their loads issued before the
 // first DMMA, keep TP x more bytes in flight (batched sweep panels, N = 10^4 x 4096 columns:
 // 0.31 -> 0.1x ms per mode).
-template <int IT, int TP, class Sink>
-__device__ __forceinline__ void kron_mode_dmma_multi(const KronView &kv, int m, const double *in, double *smat, Sink &&sink,
+template <int IT, int TP, class Load, class Sink>
+__device__ __forceinline__ void kron_mode_dmma_multi(const KronView &kv, int m, Load &&load, double *smat, Sink &&sink,
                                                      KronShare share = KronShare()) {
     constexpr int PITCH = 8 * IT + 4, KT = 2 * IT;
     const KronMode &md = kv.modes[m];
@@ -597,7 +794,7 @@ __device__ __forceinline__ void kron_mode_dmma_multi(const KronView &kv, int m, 
     for (long long seg = t_begin; seg < t_end;) {
         const long long mc = seg / tpm;
         const long long seg_end = (mc + 1) * tpm < t_end ? (mc + 1) * tpm : t_end;
-        long long rem = mc, mbase = 0;
+        long long rem = mc, mbase = md.base_off;
         int mat = 0;
         for (int a = md.nM - 1; a >= 0; --a) {
             const int c = (int)(rem % md.Mshape[a]);
@@ -610,7 +807,7 @@ __device__ __forceinline__ void kron_mode_dmma_multi(const KronView &kv, int m, 
             const double *msrc = md.mat + (long long)mat * n * n;
             for (int e = threadIdx.x; e < IT * 8 * PITCH; e += blockDim.x) {
                 const int i = e / PITCH, j = e - i * PITCH;
-                smat[e] = (i < n && j < n) ? msrc[i * n + j] : 0.0;
+                smat[e] = (i < n && j < n) ? (md.colscale ? msrc[i * n + j] * md.colscale[j] : msrc[i * n + j]) : 0.0;
             }
             __syncthreads();
             cur_mat = mat;
@@ -641,10 +838,10 @@ __device__ __forceinline__ void kron_mode_dmma_multi(const KronView &kv, int m, 
                         base[u] += c * md.Fstride[ax];
                     }
                 }
-                const double *p = in + base[u] + q * kstride;
+                long long p = base[u] + q * kstride;
 #pragma unroll
                 for (int kt = 0; kt < KT; ++kt) {
-                    a[u][kt] = (fv[u] && kt * 4 + q < n) ? *p : 0.0;
+                    a[u][kt] = (fv[u] && kt * 4 + q < n) ? load(p) : 0.0;
                     p += 4 * kstride;
                 }
             }
@@ -682,38 +879,75 @@ __device__ __forceinline__ void kron_mode_dmma_multi(const KronView &kv, int m, 
 // the persistent loop kernels keep the lean variant)
 // (SMALL_FMA: thread-per-fibre FMA contraction up to n = 16 - for vectors resident in shared memory,
 // where coalescing is moot and a warp-wide tile of only 8 fibres costs ~5x the instructions per fibre)
-template <bool PREFETCH = false, bool SMALL_FMA = false, class Sink>
-__device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const double *in, double *smat, Sink &&sink,
-                                                KronShare share = KronShare()) {
-    const int n = kv.shape[kv.modes[m].dim];
-    if (SMALL_FMA && n > 8 && n <= 16) { kron_mode_fibre<16>(kv, m, in, smat, sink, share); return; }
-    if (n < KRON_TC_MIN) kron_mode_fibre<8>(kv, m, in, smat, sink, share);      // n <= 8
+// (RECT_OK: also instantiate the restricted-output variants used by the leading mode of a slab-sharded view;
+// only call sites that may contract such a mode pay for the extra code)
+template <bool PREFETCH = false, bool SMALL_FMA = false, bool RECT_OK = false, class Load, class Sink>
+__device__ __forceinline__ void kron_mode_apply_ld(const KronView &kv, int m, Load &&load, double *smat, Sink &&sink,
+                                                   KronShare share = KronShare()) {
+    const KronMode &md = kv.modes[m];
+    const int n = kv.shape[md.dim];
+    constexpr bool HOOKS = kron_load_traits<typename kron_bare<Load>::type>::xform ||
+                           kron_sink_traits<typename kron_bare<Sink>::type>::staged;
+    if (md.nout != n) {                         // restricted output rows (validated on the host: 9 <= n <= 64)
+        if constexpr (RECT_OK) {
+            const int it_o = (md.nout + 7) >> 3;
+            if (it_o <= 1) kron_mode_dmma<1, PREFETCH, true>(kv, m, load, smat, sink, share);
+            else if (it_o <= 2) kron_mode_dmma<2, PREFETCH, true>(kv, m, load, smat, sink, share);
+            else if (it_o <= 4) kron_mode_dmma<4, PREFETCH, true>(kv, m, load, smat, sink, share);
+            else kron_mode_dmma<8, PREFETCH, true>(kv, m, load, smat, sink, share);
+        }
+        return;
+    }
+    if constexpr (SMALL_FMA) {                  // vector resident in shared memory: no cp.async staging
+        if (n > 8 && n <= 16) { kron_mode_fibre<16>(kv, m, load, smat, sink, share); return; }
+        if (n > 16 && n <= KRON_NMAX_LIMIT) {
+            const int it_s = (n + 7) >> 3;
+            if (it_s <= 4) kron_mode_dmma_reg<4, false>(kv, m, load.ptr(0), smat, sink, share);
+            else if (it_s <= 6) kron_mode_dmma_reg<6, false>(kv, m, load.ptr(0), smat, sink, share);
+            else kron_mode_dmma_reg<8, false>(kv, m, load.ptr(0), smat, sink, share);
+            return;
+        }
+    }
+    if (n < KRON_TC_MIN) kron_mode_fibre<8>(kv, m, load, smat, sink, share);      // n <= 8
     else if (n <= KRON_NMAX_LIMIT) {
         const int it_n = (n + 7) >> 3;          // 2..8 output tiles
         if constexpr (PREFETCH) {               // stand-alone kernels: exact tile count
             switch (it_n) {
-            case 2: kron_mode_dmma_multi<2, 4>(kv, m, in, smat, sink, share); break;
-            case 3: kron_mode_dmma<3, true>(kv, m, in, smat, sink, share); break;
-            case 4: kron_mode_dmma<4, true>(kv, m, in, smat, sink, share); break;
-            case 5: kron_mode_dmma<5, true>(kv, m, in, smat, sink, share); break;
-            case 6: kron_mode_dmma<6, true>(kv, m, in, smat, sink, share); break;
-            case 7: kron_mode_dmma<7, true>(kv, m, in, smat, sink, share); break;
-            default: kron_mode_dmma<8, true>(kv, m, in, smat, sink, share); break;
+            case 2:
+                if constexpr (HOOKS) kron_mode_dmma<2, true, false>(kv, m, load, smat, sink, share);
+                else kron_mode_dmma_multi<2, 4>(kv, m, load, smat, sink, share);
+                break;
+            case 3: kron_mode_dmma<3, true, false>(kv, m, load, smat, sink, share); break;
+            case 4: kron_mode_dmma<4, true, false>(kv, m, load, smat, sink, share); break;
+            case 5: kron_mode_dmma<5, true, false>(kv, m, load, smat, sink, share); break;
+            case 6: kron_mode_dmma<6, true, false>(kv, m, load, smat, sink, share); break;
+            case 7: kron_mode_dmma<7, true, false>(kv, m, load, smat, sink, share); break;
+            default: kron_mode_dmma<8, true, false>(kv, m, load, smat, sink, share); break;
             }
         } else {                                // loop kernels: even tile counts (zero-padded rows)
-            if (it_n <= 2) kron_mode_dmma_multi<2, 4>(kv, m, in, smat, sink, share);
-            else if (it_n <= 4) kron_mode_dmma<4, false>(kv, m, in, smat, sink, share);
-            else if (it_n <= 6) kron_mode_dmma<6, false>(kv, m, in, smat, sink, share);
-            else kron_mode_dmma<8, false>(kv, m, in, smat, sink, share);
+            if (it_n <= 2) {
+                if constexpr (HOOKS) kron_mode_dmma<2, false, false>(kv, m, load, smat, sink, share);
+                else kron_mode_dmma_multi<2, 4>(kv, m, load, smat, sink, share);
+            }
+            else if (it_n <= 4) kron_mode_dmma<4, false, false>(kv, m, load, smat, sink, share);
+            else if (it_n <= 6) kron_mode_dmma<6, false, false>(kv, m, load, smat, sink, share);
+            else kron_mode_dmma<8, false, false>(kv, m, load, smat, sink, share);
         }
     }
-    else kron_mode_pass(kv, m, in, (int64_t)share.cta * blockDim.x + threadIdx.x, (int64_t)share.nctas * blockDim.x, sink);
+    else kron_mode_pass(kv, m, load, (int64_t)share.cta * blockDim.x + threadIdx.x, (int64_t)share.nctas * blockDim.x, sink);
+}
+template <bool PREFETCH = false, bool SMALL_FMA = false, bool RECT_OK = false, class Sink>
+__device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const double *in, double *smat, Sink &&sink,
+                                                KronShare share = KronShare()) {
+    kron_mode_apply_ld<PREFETCH, SMALL_FMA, RECT_OK>(kv, m, KronLoadPlain{in}, smat, sink, share);
 }
 #define KRON_SMAT_DOUBLES (KRON_NMAX_LIMIT * (KRON_NMAX_LIMIT + 4))
+static_assert(KRON_NMAX_LIMIT == 64, "the restricted-output contraction stages 8 IT x (4 x 16 + 4) doubles");
 
 // Out-of-line storing contraction for the persistent loop kernels: they apply the operator at many
 // sites (T, JVP inside BiCGSTAB / GMRES, Anderson), and one shared copy of the non-final modes keeps
 // their code size (instruction-cache footprint, compile time) bounded.
-static __device__ __noinline__ void kron_mode_store(const KronView &kv, int m, const double *in, double *out, double *smat) {
-    kron_mode_apply(kv, m, in, smat, [&](int64_t idx, double s) { out[idx] = s; });
+static __device__ __noinline__ void kron_mode_store(const KronView &kv, int m, const double *in, double *out, double *smat,
+                                                    double *stage) {
+    kron_mode_apply<false, false, true>(kv, m, in, smat, [&](int64_t idx, double s) { out[idx] = s; }, KronShare(stage));
 }

@@ -46,13 +46,8 @@ def _capsule_destructor(capsule_ptr):
         lib.sdfs_dlpack_call_deleter(mt)
 
 
-_pinned_owners = {}
-
-
-def _release_pinned(key):
-    buf, ptr = _pinned_owners.pop(key, (None, None))
-    if ptr:
-        lib.sdfs_host_free_pinned(C.c_void_p(ptr))
+def _release_pinned(ptr):
+    lib.sdfs_host_free_pinned(C.c_void_p(ptr))
 
 
 class Context:
@@ -121,12 +116,13 @@ class Context:
         n = int(np.prod(shape, dtype=np.int64)) if shape else 1
         p = C.c_void_p()
         check(lib.sdfs_host_alloc_pinned(n * 8, C.byref(p)))
-        buf = (C.c_double * n).from_address(p.value)
-        arr = np.frombuffer(buf, dtype=np.float64).reshape(shape)
-        _pinned_owners[id(buf)] = (buf, p.value)
+        # the owner of the memory is the ctypes buffer object: every ndarray view (slices, reshapes;
+        # NumPy collapses .base to the frombuffer array, whose base is this buffer) keeps it alive, and
+        # the page-locked allocation is released only when the buffer object itself is collected
+        owner = type("PinnedBuffer", (C.c_double * max(n, 1),), {}).from_address(p.value)
         import weakref
-        weakref.finalize(arr, _release_pinned, id(buf))
-        return arr
+        weakref.finalize(owner, _release_pinned, p.value)
+        return np.frombuffer(owner, dtype=np.float64)[:n].reshape(shape)
 
     def asarray(self, x):
         """Host ndarray / DLPack producer / DeviceArray -> DeviceArray on this context."""
@@ -202,6 +198,21 @@ class DeviceArray:
     def __array__(self, dtype=None, copy=None):
         a = self.numpy()
         return a if dtype is None else a.astype(dtype)
+
+    def fill(self, value):
+        check(lib.sdfs_fill_f64(self.ctx.handle, self.ptr, float(value), self.size), self.ctx.handle)
+        return self
+
+    def __getitem__(self, key):
+        """Contiguous slices along the leading axis (views, no copy)."""
+        if not isinstance(key, slice) or not self.shape:
+            raise TypeError("DeviceArray supports only contiguous leading-axis slices a[i:j]")
+        i, j, step = key.indices(self.shape[0])
+        if step != 1:
+            raise TypeError("DeviceArray slices must have step 1")
+        j = max(i, j)
+        inner = int(np.prod(self.shape[1:], dtype=np.int64)) if len(self.shape) > 1 else 1
+        return DeviceArray._view(self.ctx, self.ptr.value + i * inner * 8, (j - i,) + self.shape[1:], self)
 
     def reshape(self, *shape):
         if len(shape) == 1 and hasattr(shape[0], "__len__"):

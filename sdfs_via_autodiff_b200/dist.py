@@ -21,6 +21,18 @@ def row_partition(N, nranks, rank):
     return b, min(N, b + chunk)
 
 
+def slab_partition(shapes, nranks, rank):
+    """Rows [begin, end) of a slab-sharded factor-form operator: the leading axis is cut into
+    contiguous chunks of ceil(shapes[0] / nranks) indices (the last ranks may get fewer, or none)."""
+    L = int(shapes[0])
+    inner = 1
+    for s in shapes[1:]:
+        inner *= int(s)
+    chunk = (L + nranks - 1) // nranks
+    l0 = min(L, chunk * rank)
+    return l0 * inner, min(L, l0 + chunk) * inner
+
+
 class TorchExchange:
     """bcast / allgather of small Python objects over a torch.distributed process group."""
 

@@ -15,6 +15,7 @@ from .device import Context, DeviceArray
 
 MODEL_SSY, MODEL_GCY = 0, 1
 STORAGE_DENSE, STORAGE_KRON = 0, 1
+STORAGE_KRON_LOCAL = 4     # factor form kept whole on this rank even in a multi-rank context
 _SSY_ARRAY_SHAPES = lambda s: [(s[0],), (s[0], s[0]), (s[1],), (s[1], s[1]), (s[2],), (s[2], s[2]),
                                (s[2], s[3]), (s[2], s[3], s[3]), (s[1],), (s[2],)]
 
@@ -109,7 +110,7 @@ class WCOperator:
         N = int(np.prod(factors.shapes))
         if storage == "auto":
             storage = "dense" if N <= 32768 else "kron"
-        st = {"dense": STORAGE_DENSE, "kron": STORAGE_KRON}[storage]
+        st = {"dense": STORAGE_DENSE, "kron": STORAGE_KRON, "kron_local": STORAGE_KRON_LOCAL}[storage]
         h = C.c_void_p()
         check(lib.sdfs_op_from_factors(ctx.handle, factors.handle, st, C.byref(h)), ctx.handle)
         return cls(ctx, h, factors.shapes, keep=[factors])

@@ -17,6 +17,7 @@ from .device import Context
 from .operator import Factors, WCOperator, MODEL_SSY, MODEL_GCY, STORAGE_KRON
 
 STORAGE_DENSE_REPLICATED = 2
+STORAGE_KRON_LOCAL = 4          # factor form, whole on every rank (columns, not slabs, are sharded)
 SWEEP_DENSE, SWEEP_FACTOR = 0, 1
 
 
@@ -34,7 +35,7 @@ def make_sweep_operator(model, shapes, ctx=None, form="factor"):
     kind = MODEL_GCY if hasattr(model, "ρ_ππ") else MODEL_SSY
     fac = Factors.build(kind, model.params, shapes, ctx)
     h = C.c_void_p()
-    storage = STORAGE_DENSE_REPLICATED if form == "dense" else STORAGE_KRON
+    storage = STORAGE_DENSE_REPLICATED if form == "dense" else STORAGE_KRON_LOCAL
     check(lib.sdfs_op_from_factors(ctx.handle, fac.handle, storage, C.byref(h)), ctx.handle)
     op = WCOperator(ctx, h, shapes, keep=[fac])
     check(lib.sdfs_sweep_set_form(h, SWEEP_DENSE if form == "dense" else SWEEP_FACTOR), ctx.handle)
