@@ -15,19 +15,27 @@ struct KronEpi {
         if (pa.nranks > 1) { for (int r = 0; r < pa.nranks; ++r) pa.out[r][n] = val; }
         else e.out0[n] = val;
     }
-    __device__ __forceinline__ void operator()(int64_t n, double s0, double s1) const {
-        if (e.mode == 2) apply_epilogue<true>(e, n, s0, s1);            // two outputs: local stores (gathered by the host path)
-        else put(n, epilogue_value<true>(e, n, s0, s1));
+    // per-row factor of the contraction (1 for the plain P x epilogue)
+    __device__ __forceinline__ double pre(int64_t n) const { return e.mode == 3 ? 1.0 : e.a_row[n]; }
+    // as0 = a_row s0, as1 = a_row s1 (same value when one contraction feeds the epilogue)
+    __device__ __forceinline__ void one(int64_t n, double as0, double as1) const {
+        if (e.mode == 0) put(n, 1.0 + e.beta * pow_pos(as0, e.inv_theta));
+        else if (e.mode == 1) put(n, e.beta * pow_pos(as0, e.inv_theta - 1.0) * as1);
+        else if (e.mode == 2) {          // two outputs: local stores (gathered by the host path)
+            const double bt = pow(e.beta, e.theta);
+            const double wm1 = e.w[n] - 1.0;
+            if (e.out0) e.out0[n] = bt * e.e_sdf[n] * pow_pos(wm1, 1.0 - e.theta) * (as1 / e.a_row[n]);
+            if (e.out1) e.out1[n] = bt * as0 / pow_pos(wm1, e.theta) - 1.0;
+        } else put(n, as0);
     }
-    __device__ __forceinline__ void pair(int64_t n0, int64_t n1, double s0a, double s1a, double s0b, double s1b) const {
-        if (e.mode == 0) {                  // T: two independent log/exp chains
-            const double xa = e.a_row[n0] * s0a, xb = e.a_row[n1] * s0b;
-            const double pa_ = pow_pos(xa, e.inv_theta), pb_ = pow_pos(xb, e.inv_theta);
-            put(n0, 1.0 + e.beta * pa_);
-            put(n1, 1.0 + e.beta * pb_);
+    __device__ __forceinline__ void four(int64_t n0, int64_t n1, int64_t n2, int64_t n3, double a, double b, double c, double d) const {
+        if (e.mode == 0) {                  // T: four independent log/exp chains
+            const double p0 = pow_pos(a, e.inv_theta), p1 = pow_pos(b, e.inv_theta);
+            const double p2 = pow_pos(c, e.inv_theta), p3 = pow_pos(d, e.inv_theta);
+            put(n0, 1.0 + e.beta * p0); put(n1, 1.0 + e.beta * p1);
+            put(n2, 1.0 + e.beta * p2); put(n3, 1.0 + e.beta * p3);
         } else {
-            (*this)(n0, s0a, s1a);
-            (*this)(n1, s0b, s1b);
+            one(n0, a, a); one(n1, b, b); one(n2, c, c); one(n3, d, d);
         }
     }
 };
@@ -62,7 +70,16 @@ int launch_kron_apply(sdfs_ctx *ctx, const KronView &kv, const KronApplyArgs &ka
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     KronEpi epi{e, pa};
-    void *args[] = {(void *)&kv, (void *)&ka, (void *)&epi};
+    // SDFS_KRON_TRACE=1: device timestamps at the phase boundaries of every apply, printed to stderr (diagnostic)
+    static const bool trace_on = getenv("SDFS_KRON_TRACE") && atoi(getenv("SDFS_KRON_TRACE")) != 0;
+    static unsigned long long *d_trace = nullptr;
+    KronApplyArgs ka2 = ka;
+    if (trace_on) {
+        if (!d_trace) CUDA_TRY(ctx, cudaMalloc(&d_trace, 32 * sizeof(unsigned long long)));
+        CUDA_TRY(ctx, cudaMemsetAsync(d_trace, 0, 32 * sizeof(unsigned long long), ctx->stream));
+        ka2.trace = d_trace;
+    }
+    void *args[] = {(void *)&kv, (void *)&ka2, (void *)&epi};
     const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
     if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
     CUDA_TRY(ctx, cudaLaunchCooperativeKernel((const void *)k_kron_apply, dim3((unsigned)grid), dim3(KRON_APPLY_THREADS), args,
@@ -72,6 +89,14 @@ int launch_kron_apply(sdfs_ctx *ctx, const KronView &kv, const KronApplyArgs &ka
         ctx->prof_used += 2;
     }
     ctx->launches++;
+    if (trace_on) {
+        unsigned long long h[32];
+        CUDA_TRY(ctx, cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "kron_apply trace (us per phase, grid %lld):", grid);
+        for (int i = 1; i < 32 && h[i]; ++i) fprintf(stderr, " %.1f", (h[i] - h[i - 1]) * 1e-3);
+        fprintf(stderr, "\n");
+    }
     return SDFS_OK;
 }
 

@@ -32,7 +32,16 @@ struct KronApplyArgs {
     const double *w, *v;        // operator input(s); v = direction (pmode 1) or x (pmode 3)
     double *tmp0, *tmp1;        // mode ping-pong (global element indices; a sharded rank touches its slab only)
     double *s0;                 // finished first contraction when two are needed
+    unsigned long long *trace;  // optional: globaltimer at every phase boundary (SDFS_KRON_TRACE=1), else null
 };
+
+__device__ __forceinline__ void kron_trace(const KronApplyArgs &a, int slot) {
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[slot] = t;
+    }
+}
 
 // element loader of the first contraction: the operator's prologue per element (a_col rides in the matrix)
 struct KronLoadFused {
@@ -56,25 +65,38 @@ struct KronSinkStore {
     __device__ __forceinline__ void operator()(long long idx, double s) const { out[idx] = s; }
 };
 
-// sink of the last contraction: the operator's epilogue, called from the rolled stage loop
+// sink of the last contraction: the operator's epilogue, called from the rolled stage loop.
+//   pre(idx)   the per-row factor multiplied into the contraction before the loop (a_row; all loads up front)
+//   quad(...)  up to four outputs per trip: rows idx + {0, 1, 8, 9} * stride, `left` = rows that exist from idx on
 template <class Epilogue>
 struct KronSinkEpi {
     const Epilogue &epi;
     const double *s0;           // first contraction's result when the epilogue needs two (else null)
-    __device__ __forceinline__ void operator()(long long idx, double s) const { epi(idx, s0 ? s0[idx] : s, s); }
-    __device__ __forceinline__ void pair(long long i0, long long i1, double a, double b) const {
-        epi.pair(i0, i1, s0 ? s0[i0] : a, a, s0 ? s0[i1] : b, b);
+    __device__ __forceinline__ double pre(long long idx) const { return epi.pre(idx); }
+    __device__ __forceinline__ void operator()(long long idx, double s) const {      // non-staged paths: s unscaled
+        const double f = epi.pre(idx);
+        epi.one(idx, s0 ? f * s0[idx] : f * s, f * s);
+    }
+    __device__ __forceinline__ void quad(long long idx, long long stride, double a, double b, double c, double d, int left) const {
+        const long long i1 = idx + stride, i2 = idx + 8 * stride, i3 = i2 + stride;
+        if (!s0 && left > 9) { epi.four(idx, i1, i2, i3, a, b, c, d); return; }
+        if (left > 0) epi.one(idx, s0 ? epi.pre(idx) * s0[idx] : a, a);
+        if (left > 1) epi.one(i1, s0 ? epi.pre(i1) * s0[i1] : b, b);
+        if (left > 8) epi.one(i2, s0 ? epi.pre(i2) * s0[i2] : c, c);
+        if (left > 9) epi.one(i3, s0 ? epi.pre(i3) * s0[i3] : d, d);
     }
 };
 template <class E> struct kron_sink_traits<KronSinkEpi<E>> { static constexpr bool staged = true; };
 
-// epilogue(n, s0, s1) / epilogue.pair(n0, n1, s0a, s1a, s0b, s1b) for every row n of this rank
+// epilogue.pre(n) = a_row[n]; epilogue.one(n, a_row s0, a_row s1) / epilogue.four(...) for every row n of this rank
 template <class Epilogue>
 __device__ __forceinline__ void kron_apply_device(cg::grid_group &grid, const KronView &kv, const KronApplyArgs &a,
                                                   double *smat, double *stage, Epilogue &&epilogue) {
     const int nx = (a.pmode == 1 || a.pmode == 2) ? 2 : 1;
     const int last = kv.n_modes - 1;          // >= 1 (checked on the host)
     const KronShare share(stage);
+    int slot = 0;
+    kron_trace(a, slot++);
     for (int pass = 0; pass < nx; ++pass) {
         for (int m = 0; m <= last; ++m) {
             const double *in = (m & 1) ? a.tmp0 : a.tmp1;          // mode m - 1 wrote tmp[(m - 1) & 1]
@@ -84,13 +106,16 @@ __device__ __forceinline__ void kron_apply_device(cg::grid_group &grid, const Kr
                 KronLoadFused ld{a.pmode == 3 ? 0 : ((pass == 0) ? 1 : (a.pmode == 1 ? 2 : 3)), a.pmode == 3 ? a.v : a.w, a.v, kv.theta};
                 kron_mode_apply_ld<true, false, true>(kv, 0, ld, smat, KronSinkStore{out}, share);
                 grid.sync();
+                kron_trace(a, slot++);
             } else if (m < last || (nx == 2 && pass == 0)) {
                 kron_mode_apply_ld<true, false, false>(kv, m, KronLoadPlain{in}, smat, KronSinkStore{m < last ? out : a.s0}, share);
                 grid.sync();
+                kron_trace(a, slot++);
             } else {
                 typedef typename kron_bare<Epilogue>::type EpiT;
                 KronSinkEpi<EpiT> sink{epilogue, nx == 2 ? a.s0 : nullptr};
                 kron_mode_apply_ld<true, false, false>(kv, m, KronLoadPlain{in}, smat, sink, share);
+                if (a.trace) { grid.sync(); kron_trace(a, slot++); }
             }
         }
     }

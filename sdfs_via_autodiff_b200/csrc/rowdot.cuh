@@ -524,11 +524,25 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
     typedef typename kron_bare<Sink>::type SinkT;
     constexpr bool XFORM = kron_load_traits<LoadT>::xform, STAGED = kron_sink_traits<SinkT>::staged;
     double *stw = share.stage + warp * KRON_STAGE_DOUBLES_PER_WARP + lane;     // [buf][kt][lane]
+    // free-axis decode tables in shared memory: kv.modes[m] with a run-time m is an indexed constant-bank load,
+    // and a chain of those per tile (shape, stride per axis) showed up as 20 % of the stall samples of the modes
+    __shared__ unsigned s_fshape[SDFS_MAX_DIMS];
+    __shared__ long long s_fstride[SDFS_MAX_DIMS];
+    __syncthreads();
+    if (threadIdx.x < SDFS_MAX_DIMS) {
+        s_fshape[threadIdx.x] = threadIdx.x < md.nF ? (unsigned)md.Fshape[threadIdx.x] : 1u;
+        s_fstride[threadIdx.x] = threadIdx.x < md.nF ? md.Fstride[threadIdx.x] : 0;
+    }
+    __syncthreads();
+    const int nF = md.nF;
+    const long long Fcount = md.Fcount;
     const long long tpm = (md.Fcount + 7) >> 3;              // fibre tiles per matrix combination
     const long long T = md.Mcount * tpm;
+    const double *colscale = md.colscale;
+    const double *mat0 = md.mat;
     const long long t_begin = T * share.cta / share.nctas, t_end = T * (share.cta + 1) / share.nctas;
     const long long kstride = md.stride;
-    const bool small_f = md.Fcount < (1LL << 31);            // 32-bit index decode (always, in practice)
+    const bool small_f = Fcount < (1LL << 31);            // 32-bit index decode (always, in practice)
     int cur_mat = -1;
     for (long long seg = t_begin; seg < t_end;) {
         const long long mc = seg / tpm;
@@ -543,10 +557,21 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
         }
         if (mat != cur_mat) {                   // uniform over the CTA
             __syncthreads();                    // previous matrix no longer in use
-            const double *msrc = md.mat + (long long)mat * n * n + (long long)out0 * n;
-            for (int e = threadIdx.x; e < IT * 8 * PITCH; e += blockDim.x) {
-                const int i = e / PITCH, j = e - i * PITCH;
-                smat[e] = (i < nout && j < n) ? (md.colscale ? msrc[i * n + j] * md.colscale[j] : msrc[i * n + j]) : 0.0;
+            const double *msrc = mat0 + (long long)mat * n * n + (long long)out0 * n;
+            for (int e0 = threadIdx.x; e0 < IT * 8 * PITCH; e0 += 4 * blockDim.x) {      // four loads in flight per thread
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * blockDim.x;
+                    const int i = e / PITCH, j = e - i * PITCH;
+                    v[u] = (e < IT * 8 * PITCH && i < nout && j < n) ? msrc[i * n + j] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * blockDim.x;
+                    const int j = e % PITCH;
+                    if (e < IT * 8 * PITCH) smat[e] = (colscale && j < n) ? v[u] * colscale[j] : v[u];
+                }
             }
             __syncthreads();
             cur_mat = mat;
@@ -554,21 +579,21 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
         // fragment fetch: lane (g, q) copies fibre 8 t + g at k = 4 kt + q into stage buffer `buf`
         auto fetch_tile = [&](long long t, int buf, long long &base, bool &fv) {
             const long long f = (t - mc * tpm) * 8 + g;
-            fv = f < md.Fcount;
+            fv = f < Fcount;
             base = mbase;
             if (small_f) {
                 unsigned r2 = fv ? (unsigned)f : 0u;
-                for (int ax = md.nF - 1; ax >= 0; --ax) {
-                    const unsigned sh = (unsigned)md.Fshape[ax], qd = r2 / sh;
-                    base += (long long)(r2 - qd * sh) * md.Fstride[ax];
+                for (int ax = nF - 1; ax >= 0; --ax) {
+                    const unsigned sh = s_fshape[ax], qd = r2 / sh;
+                    base += (long long)(r2 - qd * sh) * s_fstride[ax];
                     r2 = qd;
                 }
             } else {
                 long long r2 = fv ? f : 0;
-                for (int ax = md.nF - 1; ax >= 0; --ax) {
-                    const int c = (int)(r2 % md.Fshape[ax]);
-                    r2 /= md.Fshape[ax];
-                    base += c * md.Fstride[ax];
+                for (int ax = nF - 1; ax >= 0; --ax) {
+                    const int c = (int)(r2 % s_fshape[ax]);
+                    r2 /= s_fshape[ax];
+                    base += c * s_fstride[ax];
                 }
             }
             const double *p = load.ptr(base + q * kstride);
@@ -596,16 +621,23 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             double *st = stw + buf * (16 * 32);
-            if constexpr (XFORM) {              // loader arithmetic in place, rolled: two independent chains per trip
+            if constexpr (XFORM) {              // loader arithmetic in place, rolled: four independent chains per trip
                 if (fv && load.active()) {
 #pragma unroll 1
-                    for (int kt = 0; kt < kt_n; kt += 2) {
-                        const long long p0 = base + (long long)(4 * kt + q) * kstride, p1 = p0 + 4 * kstride;
-                        const bool v0 = 4 * kt + q < n, v1 = kt + 1 < kt_n && 4 * kt + 4 + q < n;
-                        double x0 = st[kt * 32], x1 = v1 ? st[(kt + 1) * 32] : 0.0;
-                        if (v1) { x0 = load.xform(p0, x0); x1 = load.xform(p1, x1); st[(kt + 1) * 32] = x1; }
-                        else if (v0) x0 = load.xform(p0, x0);
-                        st[kt * 32] = x0;
+                    for (int kt = 0; kt < kt_n; kt += 4) {
+                        double x[4];
+                        bool v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            v[u] = kt + u < kt_n && 4 * (kt + u) + q < n;
+                            x[u] = v[u] ? st[(kt + u) * 32] : 1.0;
+                        }
+                        const long long p0 = base + (long long)(4 * kt + q) * kstride;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) x[u] = load.xform(v[u] ? p0 + 4LL * u * kstride : p0, x[u]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (v[u]) st[(kt + u) * 32] = x[u];
                     }
                 }
             }
@@ -622,19 +654,31 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
                     for (int it = 0; it < IT; ++it) dmma884(c[it][0], c[it][1], a, brow[it * 8 * PITCH + kt * 4]);
                 }
             }
-            if constexpr (STAGED) {               // sink arithmetic from the stage, rolled (two outputs per trip)
-#pragma unroll
-                for (int it = 0; it < IT; ++it) { st[(2 * it) * 32] = c[it][0]; st[(2 * it + 1) * 32] = c[it][1]; }
+            if constexpr (STAGED) {               // sink arithmetic from the stage, rolled (four outputs per trip)
+                // the sink's per-row factor (a_row) for all 2 IT outputs first: every load in flight at once
+                // instead of one exposed latency per trip; c is dead after this block
                 if (fv) {
                     long long idx = base + (out0 + 2 * q) * kstride;
+                    double f[IT][2];
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) {
+                        const int i = it * 8 + 2 * q;
+                        f[it][0] = i < nout ? sink.pre(idx) : 1.0;
+                        f[it][1] = i + 1 < nout ? sink.pre(idx + kstride) : 1.0;
+                        idx += 8 * kstride;
+                    }
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) { st[(2 * it) * 32] = c[it][0] * f[it][0]; st[(2 * it + 1) * 32] = c[it][1] * f[it][1]; }
+                    idx = base + (out0 + 2 * q) * kstride;
                     const int it_o = (nout + 7) >> 3;
 #pragma unroll 1
-                    for (int it = 0; it < it_o; ++it) {
+                    for (int it = 0; it < it_o; it += 2) {
                         const int i = it * 8 + 2 * q;
                         const double s0 = st[(2 * it) * 32], s1 = st[(2 * it + 1) * 32];
-                        if (i + 1 < nout) sink.pair(idx, idx + kstride, s0, s1);
-                        else if (i < nout) sink(idx, s0);
-                        idx += 8 * kstride;
+                        const double s2 = st[(2 * it + 2) * 32], s3 = st[(2 * it + 3) * 32];
+                        // rows i, i+1, i+8, i+9 (the last ones may not exist)
+                        sink.quad(idx, kstride, s0, s1, s2, s3, nout - i);
+                        idx += 16 * kstride;
                     }
                 }
             } else if (fv) {
