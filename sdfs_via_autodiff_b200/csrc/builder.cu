@@ -284,12 +284,14 @@ int factors_to_kron(const sdfs_factors *f, KronView *kv) {
         // contraction order of the sum-factorised apply: l' (Q_lam) first -- the leading axis is the one a
         // multi-GPU run splits into slabs, and contracting it first is the only step that needs the other
         // ranks' part of the input, so everything after it is rank-local (the same order on one GPU keeps
-        // results bit-identical across rank counts) -- then i' (Q_hz), j' (z_Q[i], needs the current i), k' (Q_c)
+        // results bit-identical across rank counts) -- then k' (Q_c), i' (Q_hz) and last j' (z_Q[i], which needs
+        // the current i): the last contraction runs along the innermost axis, so a finished fibre is one
+        // contiguous run of outputs (wide stores in the fused epilogue, also into the peers' result buffers)
         kv->n_modes = 4;
         kv->modes[0].mat = f->d_arr[1]; kv->modes[0].dim = 0;
-        kv->modes[1].mat = f->d_arr[5]; kv->modes[1].dim = 2;
-        kv->modes[2].mat = f->d_arr[7]; kv->modes[2].dim = 3; kv->modes[2].mstride[2] = 1;
-        kv->modes[3].mat = f->d_arr[3]; kv->modes[3].dim = 1;
+        kv->modes[1].mat = f->d_arr[3]; kv->modes[1].dim = 1;
+        kv->modes[2].mat = f->d_arr[5]; kv->modes[2].dim = 2;
+        kv->modes[3].mat = f->d_arr[7]; kv->modes[3].dim = 3; kv->modes[3].mstride[2] = 1;
     } else {
         const int nhz = f->shapes[2], nhzp = f->shapes[4];
         kv->n_modes = 6;

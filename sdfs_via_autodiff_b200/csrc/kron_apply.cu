@@ -28,15 +28,23 @@ struct KronEpi {
             if (e.out1) e.out1[n] = bt * as0 / pow_pos(wm1, e.theta) - 1.0;
         } else put(n, as0);
     }
-    __device__ __forceinline__ void four(int64_t n0, int64_t n1, int64_t n2, int64_t n3, double a, double b, double c, double d) const {
-        if (e.mode == 0) {                  // T: four independent log/exp chains
-            const double p0 = pow_pos(a, e.inv_theta), p1 = pow_pos(b, e.inv_theta);
-            const double p2 = pow_pos(c, e.inv_theta), p3 = pow_pos(d, e.inv_theta);
-            put(n0, 1.0 + e.beta * p0); put(n1, 1.0 + e.beta * p1);
-            put(n2, 1.0 + e.beta * p2); put(n3, 1.0 + e.beta * p3);
-        } else {
-            one(n0, a, a); one(n1, b, b); one(n2, c, c); one(n3, d, d);
-        }
+    __device__ __forceinline__ bool single_output() const { return e.mode != 2; }
+    __device__ __forceinline__ void put2(int64_t n, double v0, double v1) const {      // n even: one 16-byte store per rank
+        const double2 v = make_double2(v0, v1);
+        if (pa.nranks > 1) { for (int r = 0; r < pa.nranks; ++r) *reinterpret_cast<double2 *>(pa.out[r] + n) = v; }
+        else *reinterpret_cast<double2 *>(e.out0 + n) = v;
+    }
+    // four single-output epilogues at once (independent log/exp chains): (as0, as1) pairs in, results in as1
+    __device__ __forceinline__ void values4(double a0, double &a, double b0, double &b, double c0, double &c, double d0, double &d) const {
+        if (e.mode == 0) {
+            const double p0 = pow_pos(a0, e.inv_theta), p1 = pow_pos(b0, e.inv_theta);
+            const double p2 = pow_pos(c0, e.inv_theta), p3 = pow_pos(d0, e.inv_theta);
+            a = 1.0 + e.beta * p0; b = 1.0 + e.beta * p1; c = 1.0 + e.beta * p2; d = 1.0 + e.beta * p3;
+        } else if (e.mode == 1) {
+            const double ex = e.inv_theta - 1.0;
+            const double p0 = pow_pos(a0, ex), p1 = pow_pos(b0, ex), p2 = pow_pos(c0, ex), p3 = pow_pos(d0, ex);
+            a = e.beta * p0 * a; b = e.beta * p1 * b; c = e.beta * p2 * c; d = e.beta * p3 * d;
+        }                                   // mode 3 (plain P x): the values are the contractions themselves
     }
 };
 

@@ -77,9 +77,26 @@ struct KronSinkEpi {
         const double f = epi.pre(idx);
         epi.one(idx, s0 ? f * s0[idx] : f * s, f * s);
     }
+    __device__ __forceinline__ bool single_output() const { return epi.single_output(); }
+    __device__ __forceinline__ void store1(long long idx, double v) const { epi.put(idx, v); }
+    __device__ __forceinline__ void store2(long long idx, double v0, double v1) const { epi.put2(idx, v0, v1); }
+    // single-output epilogues as values: a..d (pre-scaled contractions of rows idx + {0, 1, 8, 9} stride) are
+    // replaced by the results; rows that do not exist (left <= 0, 1, 8, 9) get harmless inputs
+    __device__ __forceinline__ void values(long long idx, long long stride, double &a, double &b, double &c, double &d, int left) const {
+        const long long i1 = idx + stride, i2 = idx + 8 * stride, i3 = i2 + stride;
+        double a0 = a, b0 = b, c0 = c, d0 = d;                 // first contraction (scaled) when two feed the epilogue
+        if (s0) {
+            a0 = left > 0 ? epi.pre(idx) * s0[idx] : 1.0; b0 = left > 1 ? epi.pre(i1) * s0[i1] : 1.0;
+            c0 = left > 8 ? epi.pre(i2) * s0[i2] : 1.0; d0 = left > 9 ? epi.pre(i3) * s0[i3] : 1.0;
+        }
+        if (left <= 1) { b = 1.0; b0 = 1.0; }
+        if (left <= 8) { c = 1.0; c0 = 1.0; }
+        if (left <= 9) { d = 1.0; d0 = 1.0; }
+        epi.values4(a0, a, b0, b, c0, c, d0, d);
+    }
+    // multi-output epilogues (SDF): store from here
     __device__ __forceinline__ void quad(long long idx, long long stride, double a, double b, double c, double d, int left) const {
         const long long i1 = idx + stride, i2 = idx + 8 * stride, i3 = i2 + stride;
-        if (!s0 && left > 9) { epi.four(idx, i1, i2, i3, a, b, c, d); return; }
         if (left > 0) epi.one(idx, s0 ? epi.pre(idx) * s0[idx] : a, a);
         if (left > 1) epi.one(i1, s0 ? epi.pre(i1) * s0[i1] : b, b);
         if (left > 8) epi.one(i2, s0 ? epi.pre(i2) * s0[i2] : c, c);

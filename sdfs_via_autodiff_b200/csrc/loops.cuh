@@ -40,6 +40,7 @@ struct LoopStatus {        // lives in ctx->d_status (4 KB)
     double final_err;
     unsigned long long epoch_end;   // barrier epoch after the loop (identical on all ranks)
     double pad[2];
+    unsigned long long t_apply_ns, n_apply, t_total_ns, t_mode_ns[4];   // block 0's clock: time inside operator applications (diagnostic)
     double outer_err[HIST_CAP];
     long long inner_iters[HIST_CAP];
 };
@@ -53,6 +54,12 @@ struct LoopEnv {
     double *xin[SDFS_MAX_RANKS][2];              // matvec input buffers of rank r
     LoopStatus *status;
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ---- device-side synchronisation and reductions ---------------------------
 // Barrier across every CTA of every rank.  Returns false (uniformly) after a peer
@@ -248,13 +255,19 @@ struct KronLoopOp {
     __device__ __forceinline__ bool apply(cg::grid_group &grid, const LoopEnv &env, unsigned long long &epoch,
                                           Scratch &sc, const double *xin, const double *, Epi &&epi) const {
         const double *in = xin;
+        const bool clk = blockIdx.x == 0 && threadIdx.x == 0;
+        unsigned long long t0 = 0, t1;
+        if (clk) t0 = gtimer();
+        const unsigned long long tb = t0;
         for (int m = 0; m < kv.n_modes - 1; ++m) {
             double *out = (m & 1) ? tmp1 : tmp0;
             kron_mode_store(kv, m, in, out, sc.smat, sc.stage);
             if (!all_sync(grid, env, epoch)) return false;
+            if (clk) { t1 = gtimer(); if (m < 3) env.status->t_mode_ns[m] += t1 - t0; t0 = t1; }
             in = out;
         }
         kron_mode_apply(kv, kv.n_modes - 1, in, sc.smat, [&](int64_t idx, double s) { epi(idx, s); }, KronShare(sc.stage));
+        if (clk) { t1 = gtimer(); env.status->t_mode_ns[3] += t1 - t0; env.status->t_apply_ns += t1 - tb; env.status->n_apply += 1; }
         return true;
     }
 };
@@ -640,6 +653,7 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_newton_loop(co
 
     long long it = 0, inner_total = 0, matvecs = 0;
     double error = a.tol + 1.0;
+    const unsigned long long t_begin = gtimer();
     while (error > a.tol && it < a.max_iter) {
         // B: s = a_row P xin ; Tw ; g = Tw - w ; d ; Krylov init ; <g,g>
         double vb[1] = {0.0};
@@ -685,6 +699,7 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_newton_loop(co
         env.status->final_err = error;
         env.status->inner_total = inner_total;
         env.status->matvecs = matvecs;
+        env.status->t_total_ns = gtimer() - t_begin;
         env.status->epoch_end = epoch;
     }
 }

@@ -669,17 +669,54 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
                     }
 #pragma unroll
                     for (int it = 0; it < IT; ++it) { st[(2 * it) * 32] = c[it][0] * f[it][0]; st[(2 * it + 1) * 32] = c[it][1] * f[it][1]; }
-                    idx = base + (out0 + 2 * q) * kstride;
+                }
+                // innermost-axis mode with a single-output sink: the values go back into the stage and the warp
+                // stores each fibre's nout contiguous outputs with 16-byte stores (448 contiguous bytes per fibre
+                // at n = 56 instead of 8-byte stores in 64-byte pieces: what NVLink peer stores and HBM both want)
+                const bool wide = kstride == 1 && sink.single_output();
+                if (fv) {
+                    long long idx = base + (out0 + 2 * q) * kstride;
                     const int it_o = (nout + 7) >> 3;
 #pragma unroll 1
                     for (int it = 0; it < it_o; it += 2) {
                         const int i = it * 8 + 2 * q;
-                        const double s0 = st[(2 * it) * 32], s1 = st[(2 * it + 1) * 32];
-                        const double s2 = st[(2 * it + 2) * 32], s3 = st[(2 * it + 3) * 32];
+                        double s0 = st[(2 * it) * 32], s1 = st[(2 * it + 1) * 32];
+                        double s2 = st[(2 * it + 2) * 32], s3 = st[(2 * it + 3) * 32];
                         // rows i, i+1, i+8, i+9 (the last ones may not exist)
-                        sink.quad(idx, kstride, s0, s1, s2, s3, nout - i);
+                        if (!sink.single_output()) {
+                            sink.quad(idx, kstride, s0, s1, s2, s3, nout - i);
+                        } else {
+                            sink.values(idx, kstride, s0, s1, s2, s3, nout - i);
+                            if (wide) {
+                                st[(2 * it) * 32] = s0; st[(2 * it + 1) * 32] = s1;
+                                st[(2 * it + 2) * 32] = s2; st[(2 * it + 3) * 32] = s3;
+                            } else {
+                                const int left = nout - i;
+                                if (left > 0) sink.store1(idx, s0);
+                                if (left > 1) sink.store1(idx + kstride, s1);
+                                if (left > 8) sink.store1(idx + 8 * kstride, s2);
+                                if (left > 9) sink.store1(idx + 9 * kstride, s3);
+                            }
+                        }
                         idx += 16 * kstride;
                     }
+                }
+                if (wide) {
+                    __syncwarp();
+                    const double *sw = st - lane;                     // this warp's stage buffer, all lanes' columns
+#pragma unroll 1
+                    for (int f8 = 0; f8 < 8; ++f8) {
+                        const long long bf = __shfl_sync(0xffffffffu, base, 4 * f8) + out0;
+                        const int vf = __shfl_sync(0xffffffffu, (int)fv, 4 * f8);
+                        const int i0 = 2 * lane;
+                        if (vf && i0 < nout) {
+                            const int it = i0 >> 3, qq = (i0 & 7) >> 1;
+                            const double v0 = sw[(2 * it) * 32 + 4 * f8 + qq], v1 = sw[(2 * it + 1) * 32 + 4 * f8 + qq];
+                            if (i0 + 1 < nout && ((bf & 1) == 0)) sink.store2(bf + i0, v0, v1);
+                            else { sink.store1(bf + i0, v0); if (i0 + 1 < nout) sink.store1(bf + i0 + 1, v1); }
+                        }
+                    }
+                    __syncwarp();
                 }
             } else if (fv) {
                 long long idx = base + (out0 + 2 * q) * kstride;

@@ -217,6 +217,11 @@ class DeviceArray:
     def reshape(self, *shape):
         if len(shape) == 1 and hasattr(shape[0], "__len__"):
             shape = tuple(shape[0])
+        if -1 in shape:                          # one inferred axis, like NumPy
+            known = int(np.prod([s for s in shape if s != -1], dtype=np.int64))
+            if list(shape).count(-1) != 1 or known == 0 or self.size % known:
+                raise ValueError(f"cannot reshape {self.shape} to {shape}")
+            shape = tuple(self.size // known if s == -1 else s for s in shape)
         if int(np.prod(shape, dtype=np.int64)) != self.size:
             raise ValueError(f"cannot reshape {self.shape} to {shape}")
         return DeviceArray._view(self.ctx, self.ptr.value, shape, self)

@@ -149,11 +149,16 @@ class WCOperator:
             raise ValueError(f"array of size {d.size} given to an operator with N={self.N}")
         return d
 
-    def __call__(self, w):
+    def __call__(self, w, out=None):
+        """One evaluation of T.  ``out`` (optional, an extension): a DeviceArray of N elements to write
+        into instead of allocating the result (must not alias ``w``)."""
         if isinstance(w, _Probe):
             return _ProbeResult(self)
         d = self._in(w)
-        out = self.ctx.empty(self.shapes)
+        if out is None:
+            out = self.ctx.empty(self.shapes)
+        elif not isinstance(out, DeviceArray) or out.size != self.N or out.ptr.value == d.ptr.value:
+            raise ValueError("out must be a DeviceArray of N elements distinct from the input")
         check(lib.sdfs_op_apply_T(self.handle, d.ptr, out.ptr), self.ctx.handle)
         return out
 
