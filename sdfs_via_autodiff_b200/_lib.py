@@ -18,7 +18,25 @@ class SdfsError(RuntimeError):
         self.code = code
 
 
+def _point_at_nccl():
+    """libsdfs_b200 dlopens NCCL lazily (multi-GPU contexts only).  Tell it where the NCCL wheel of this
+    environment lives unless the caller already did; nothing is imported (torch stays optional)."""
+    if os.environ.get("SDFS_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["SDFS_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def _load():
+    _point_at_nccl()
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found. Build it with `python sdfs_via_autodiff_b200/build.py` "

@@ -37,30 +37,39 @@ int sdfs_ctx_create(int device, sdfs_ctx **out) {
                               device, ndev);
     sdfs_ctx *ctx = new sdfs_ctx();
     ctx->device = device;
-    CUDA_TRY(nullptr, cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-        delete ctx;
-        return sdfs_set_error(nullptr, SDFS_ERR_UNSUPPORTED,
-                              "sdfs_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
-                              device, prop.major, prop.minor);
+    // every failure below releases what was created so far (sdfs_ctx_destroy tolerates null members)
+    auto init = [&]() -> int {
+        CUDA_TRY(nullptr, cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            return sdfs_set_error(nullptr, SDFS_ERR_UNSUPPORTED,
+                                  "sdfs_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                                  device, prop.major, prop.minor);
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->coop_supported = prop.cooperativeLaunch;
+        CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        {
+            cudaMemPool_t pool;
+            CUDA_TRY(nullptr, cudaDeviceGetDefaultMemPool(&pool, device));
+            uint64_t keep = ~0ull;   // keep freed blocks cached in the pool
+            CUDA_TRY(nullptr, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        CUDA_TRY(nullptr, cudaEventCreate(&ctx->ev0));
+        CUDA_TRY(nullptr, cudaEventCreate(&ctx->ev1));
+        CUDA_TRY(nullptr, cudaMalloc(&ctx->d_status, 4096));
+        CUDA_TRY(nullptr, cudaMemset(ctx->d_status, 0, 4096));
+        CUDA_TRY(nullptr, cudaMallocHost(&ctx->h_status, 4096));
+        memset(ctx->h_status, 0, 4096);
+        return SDFS_OK;
+    };
+    const int rc = init();
+    if (rc != SDFS_OK) {
+        const std::string msg = g_last_error;        // sdfs_ctx_destroy must not clobber the reason
+        sdfs_ctx_destroy(ctx);
+        g_last_error = msg;
+        return rc;
     }
-    ctx->sm_count = prop.multiProcessorCount;
-    ctx->coop_supported = prop.cooperativeLaunch;
-    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    {
-        cudaMemPool_t pool;
-        CUDA_TRY(nullptr, cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t keep = ~0ull;   // keep freed blocks cached in the pool
-        CUDA_TRY(nullptr, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    }
-    CUDA_TRY(nullptr, cudaEventCreate(&ctx->ev0));
-    CUDA_TRY(nullptr, cudaEventCreate(&ctx->ev1));
-    CUDA_TRY(nullptr, cudaMalloc(&ctx->d_status, 4096));
-    CUDA_TRY(nullptr, cudaMemset(ctx->d_status, 0, 4096));
-    CUDA_TRY(nullptr, cudaMallocHost(&ctx->h_status, 4096));
-    memset(ctx->h_status, 0, 4096);
     *out = ctx;
     return SDFS_OK;
 }
@@ -68,14 +77,14 @@ int sdfs_ctx_create(int device, sdfs_ctx **out) {
 int sdfs_ctx_destroy(sdfs_ctx *ctx) {
     if (!ctx) return SDFS_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     comm_destroy(ctx);
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
-    cudaEventDestroy(ctx->ev0);
-    cudaEventDestroy(ctx->ev1);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t ev : ctx->prof_ev) cudaEventDestroy(ev);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SDFS_OK;
 }
@@ -87,7 +96,7 @@ int sdfs_ctx_sync(sdfs_ctx *ctx) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (*(volatile long long *)ctx_h_abort(ctx))
-        return sdfs_set_error(ctx, SDFS_ERR_TIMEOUT, "a peer rank did not reach a fused exchange (30 s device-side timeout)");
+        return sdfs_set_error(ctx, SDFS_ERR_TIMEOUT, "a peer rank did not reach a fused exchange (30 s device-side timeout); the context's exchange state is poisoned: destroy and re-create the contexts of all ranks");
     return SDFS_OK;
 }
 
@@ -125,7 +134,7 @@ int sdfs_timer_stop_ms(sdfs_ctx *ctx, double *ms) {
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
     if (*(volatile long long *)ctx_h_abort(ctx))
-        return sdfs_set_error(ctx, SDFS_ERR_TIMEOUT, "a peer rank did not reach a fused exchange (30 s device-side timeout)");
+        return sdfs_set_error(ctx, SDFS_ERR_TIMEOUT, "a peer rank did not reach a fused exchange (30 s device-side timeout); the context's exchange state is poisoned: destroy and re-create the contexts of all ranks");
     float f = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
     *ms = (double)f;
@@ -201,7 +210,7 @@ int sdfs_d2h(sdfs_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
     CUDA_TRY(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (*(volatile long long *)ctx_h_abort(ctx))
-        return sdfs_set_error(ctx, SDFS_ERR_TIMEOUT, "a peer rank did not reach a fused exchange (30 s device-side timeout)");
+        return sdfs_set_error(ctx, SDFS_ERR_TIMEOUT, "a peer rank did not reach a fused exchange (30 s device-side timeout); the context's exchange state is poisoned: destroy and re-create the contexts of all ranks");
     return SDFS_OK;
 }
 

@@ -30,12 +30,13 @@ static NcclApi g_nccl;
 
 static int nccl_load(sdfs_ctx *ctx) {
     if (g_nccl.lib) return SDFS_OK;
-    const char *cands[4] = {getenv("SDFS_NCCL_LIB"),
-                            "/opt/prime-rl/.venv/lib/python3.12/site-packages/nvidia/nccl/lib/libnccl.so.2",
-                            "libnccl.so.2", "libnccl.so"};
+    // SDFS_NCCL_LIB (the Python package points it at the NCCL wheel it finds, _lib.py), else a libnccl this
+    // process has already loaded (torch), else the loader path - no image-specific path is compiled in
     void *h = nullptr;
-    for (int i = 0; i < 4 && !h; ++i)
-        if (cands[i]) h = dlopen(cands[i], RTLD_NOW | RTLD_GLOBAL);
+    if (const char *envp = getenv("SDFS_NCCL_LIB")) h = dlopen(envp, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!h) return sdfs_set_error(ctx, SDFS_ERR_COMM, "cannot load libnccl.so.2 (set SDFS_NCCL_LIB): %s", dlerror());
 #define SYM(field, name)                                                                     \
     *(void **)(&g_nccl.field) = dlsym(h, name);                                              \
@@ -79,6 +80,13 @@ int comm_destroy(sdfs_ctx *ctx) {
     if (cs->peers_mapped)
         for (int r = 0; r < ctx->nranks; ++r)
             if (r != ctx->rank && cs->peer_arena[r]) cudaIpcCloseMemHandle(cs->peer_arena[r]);
+    // peers may still be storing into this arena: a collective barrier first (skipped when the exchange state is
+    // poisoned by a peer timeout - the peer is gone - or when SDFS_COMM_DESTROY_BARRIER=0)
+    static const bool barrier_on = !(getenv("SDFS_COMM_DESTROY_BARRIER") && atoi(getenv("SDFS_COMM_DESTROY_BARRIER")) == 0);
+    if (cs->comm && cs->peers_mapped && barrier_on && ctx->h_status && !*(volatile long long *)ctx_h_abort(ctx)) {
+        double *tmp = (double *)ctx->d_status + 256;
+        if (g_nccl.AllReduce(tmp, tmp, 1, ncclFloat64, ncclSumOp, cs->comm, ctx->stream) == 0) cudaStreamSynchronize(ctx->stream);
+    }
     if (cs->arena) cudaFree(cs->arena);
     if (cs->comm) g_nccl.CommDestroy(cs->comm);
     delete cs;

@@ -43,10 +43,14 @@ static int finish_loop(sdfs_ctx *ctx, LoopStatus *hs, unsigned long long epochs_
         return sdfs_set_error(ctx, SDFS_ERR_TIMEOUT, "device loop aborted: a peer rank did not reach the barrier");
     static const bool trace = getenv("SDFS_LOOP_TRACE") && atoi(getenv("SDFS_LOOP_TRACE")) != 0;
     if (trace && hs->n_apply)
-        fprintf(stderr, "loop trace: %llu factor-form applications, %.1f us each inside the operator (modes %.1f %.1f %.1f %.1f), "
-                        "loop total %.3f ms\n", hs->n_apply, hs->t_apply_ns * 1e-3 / hs->n_apply,
+        fprintf(stderr, "loop trace: %llu factor-form applications, %.1f us each inside the operator (modes %.1f %.1f %.1f %.1f, "
+                        "epilogue phase %.1f), loop total %.3f ms\n", hs->n_apply, hs->t_apply_ns * 1e-3 / hs->n_apply,
                 hs->t_mode_ns[0] * 1e-3 / hs->n_apply, hs->t_mode_ns[1] * 1e-3 / hs->n_apply, hs->t_mode_ns[2] * 1e-3 / hs->n_apply,
-                hs->t_mode_ns[3] * 1e-3 / hs->n_apply, hs->t_total_ns * 1e-6);
+                hs->t_mode_ns[3] * 1e-3 / hs->n_apply, hs->t_epi_ns * 1e-3 / hs->n_apply, hs->t_total_ns * 1e-6);
+    if (trace && hs->n_apply && hs->t_vec_ns[0])
+        fprintf(stderr, "loop trace: BiCGSTAB vector phases per application: C %.1f us, E (+reduction) %.1f, G (+reduction) %.1f, reduction after D %.1f\n",
+                hs->t_vec_ns[0] * 1e-3 / hs->n_apply, hs->t_vec_ns[1] * 1e-3 / hs->n_apply, hs->t_vec_ns[2] * 1e-3 / hs->n_apply,
+                hs->t_red_ns * 1e-3 / hs->n_apply);
     return SDFS_OK;
 }
 

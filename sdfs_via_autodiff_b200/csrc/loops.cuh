@@ -29,6 +29,7 @@ int small_sa_try(sdfs_op *op, const double *d_w_init, double tol, int64_t max_it
 #define TRY(x) do { int _rc = (x); if (_rc != SDFS_OK) return _rc; } while (0)
 
 #define HIST_CAP 120       // outer Newton iterations recorded in the status page
+#define VU 4               // elements per thread and trip in the Krylov vector phases
 #define GMRES_MAX_RESTART 64
 #define GMRES_WS_BYTES (((GMRES_MAX_RESTART + 1) * 2 + GMRES_MAX_RESTART * 3 + GMRES_MAX_RESTART * GMRES_MAX_RESTART) * sizeof(double) + 16)
 
@@ -40,7 +41,7 @@ struct LoopStatus {        // lives in ctx->d_status (4 KB)
     double final_err;
     unsigned long long epoch_end;   // barrier epoch after the loop (identical on all ranks)
     double pad[2];
-    unsigned long long t_apply_ns, n_apply, t_total_ns, t_mode_ns[4];   // block 0's clock: time inside operator applications (diagnostic)
+    unsigned long long t_apply_ns, n_apply, t_total_ns, t_mode_ns[4], t_epi_ns, t_vec_ns[3], t_red_ns;   // block 0's clock: time inside operator applications (diagnostic)
     double outer_err[HIST_CAP];
     long long inner_iters[HIST_CAP];
 };
@@ -251,6 +252,13 @@ struct KronLoopOp {
                                             Scratch &sc, const double *xin, Epi &&epi) const {
         return apply(grid, env, epoch, sc, xin, nullptr, [&](int64_t n, double s) { epi(n, kv.a_row[n] * s); });
     }
+    // Every mode is contracted by the one out-of-line storing function (exact tile counts, cp.async-staged
+    // fragments), the barriers between modes are LOCAL grid barriers (only the first mode reads data written
+    // by other ranks, and that was ordered by the all_sync before the call), and the epilogue runs as a
+    // coalesced vector phase over the finished contraction.  (Fused into the last contraction's sink, as in
+    // round 1, the epilogue's scattered dependent loads - d, p, r-hat per output - made that mode cost 169 us
+    // against 68 us for the others at 9.8 M states, and every call site carried its own copy of the
+    // tensor-core code.)
     template <class Epi>
     __device__ __forceinline__ bool apply(cg::grid_group &grid, const LoopEnv &env, unsigned long long &epoch,
                                           Scratch &sc, const double *xin, const double *, Epi &&epi) const {
@@ -259,15 +267,32 @@ struct KronLoopOp {
         unsigned long long t0 = 0, t1;
         if (clk) t0 = gtimer();
         const unsigned long long tb = t0;
-        for (int m = 0; m < kv.n_modes - 1; ++m) {
+        for (int m = 0; m < kv.n_modes; ++m) {
             double *out = (m & 1) ? tmp1 : tmp0;
             kron_mode_store(kv, m, in, out, sc.smat, sc.stage);
-            if (!all_sync(grid, env, epoch)) return false;
-            if (clk) { t1 = gtimer(); if (m < 3) env.status->t_mode_ns[m] += t1 - t0; t0 = t1; }
+            __threadfence();
+            grid.sync();
+            if (clk) { t1 = gtimer(); if (m < 4) env.status->t_mode_ns[m] += t1 - t0; t0 = t1; }
             in = out;
         }
-        kron_mode_apply(kv, kv.n_modes - 1, in, sc.smat, [&](int64_t idx, double s) { epi(idx, s); }, KronShare(sc.stage));
-        if (clk) { t1 = gtimer(); env.status->t_mode_ns[3] += t1 - t0; env.status->t_apply_ns += t1 - tb; env.status->n_apply += 1; }
+        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+        const int64_t rb = kv.row_begin, re = kv.row_end;
+        for (int64_t n0 = rb + tid; n0 < re; n0 += VU * nth) {
+            double sv[VU];
+#pragma unroll
+            for (int u = 0; u < VU; ++u) {
+                const int64_t n = n0 + u * nth;
+                sv[u] = n < re ? in[n] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < VU; ++u) {
+                const int64_t n = n0 + u * nth;
+                if (n < re) epi(n, sv[u]);
+            }
+        }
+        if (clk) { t1 = gtimer(); env.status->t_epi_ns += t1 - t0; env.status->t_apply_ns += t1 - tb; env.status->n_apply += 1; }
+        (void)env; (void)epoch;
         return true;
     }
 };
@@ -355,7 +380,7 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_sa_loop(const 
         if (!ok) return;
         if (!grid_allreduce<1, true>(grid, env, epoch, (int)(it & 1), part, smem)) return;
         error = part[0];
-        if (tid == 0 && env.rank == 0 && a.err_hist && (it % a.hist_stride) == 0 && (it / a.hist_stride) < a.hist_cap)
+        if (tid == 0 && a.err_hist && (it % a.hist_stride) == 0 && (it / a.hist_stride) < a.hist_cap)   // every rank: its own buffer, identical values
             a.err_hist[it / a.hist_stride] = error;
         ++it;
     }
@@ -375,7 +400,8 @@ struct NewtonArgs {
     const double *w_init;
     double *w_out;
     // N-vectors (full length allocations; each rank touches its own rows)
-    double *w, *g, *c, *d, *x, *r, *rhat, *p, *q, *s, *t;
+    double *__restrict__ w, *__restrict__ g, *__restrict__ c, *__restrict__ d, *__restrict__ x, *__restrict__ r,
+        *__restrict__ rhat, *__restrict__ p, *__restrict__ q, *__restrict__ s, *__restrict__ t;   // distinct work vectors
     double *V;             // GMRES basis: (restart+1) vectors of ldv doubles
     long long ldv;
     double tol;
@@ -407,12 +433,30 @@ __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &
         // C: p = r + beta (p - omega q); xin = c .* p
         const double rho_ = rho_next;
         const double beta = rho_ / rho * alpha / omega;
-        for (int64_t n = rb + tid; n < re; n += nth) {
-            const double pn = a.r[n] + beta * (a.p[n] - omega * a.q[n]);
-            a.p[n] = pn;
-            store_all_ranks(env, 0, n, a.c[n] * pn);
+        const bool clk = blockIdx.x == 0 && threadIdx.x == 0;
+        unsigned long long tp = 0, tq = 0;
+        if (clk) tp = gtimer();
+        // (vector phases: VU independent elements per trip, every load issued before the first store - one
+        // element per trip left the loops latency-bound at ~half of HBM bandwidth with 18 warps per SM)
+        for (int64_t n0 = rb + tid; n0 < re; n0 += VU * nth) {
+            double rv[VU], pv[VU], qv[VU], cv[VU];
+#pragma unroll
+            for (int u = 0; u < VU; ++u) {
+                const int64_t n = n0 + u * nth;
+                if (n < re) { rv[u] = a.r[n]; pv[u] = a.p[n]; qv[u] = a.q[n]; cv[u] = a.c[n]; }
+            }
+#pragma unroll
+            for (int u = 0; u < VU; ++u) {
+                const int64_t n = n0 + u * nth;
+                if (n < re) {
+                    const double pn = rv[u] + beta * (pv[u] - omega * qv[u]);
+                    a.p[n] = pn;
+                    store_all_ranks(env, 0, n, cv[u] * pn);
+                }
+            }
         }
         if (!all_sync(grid, env, epoch)) return false;
+        if (clk) { tq = gtimer(); env.status->t_vec_ns[0] += tq - tp; }
         // D: q = J p = d .* P(c .* p) - p ; <rhat,q>
         double v1[1] = {0.0};
         if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], env.xin[env.rank][1], [&](int64_t n, double sum) {
@@ -420,17 +464,32 @@ __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &
                 a.q[n] = qn;
                 v1[0] += a.rhat[n] * qn;
             })) return false;
+        if (clk) tp = gtimer();
         if (!grid_allreduce<1, false>(grid, env, epoch, SET_D, v1, smem)) return false;
+        if (clk) { tq = gtimer(); env.status->t_red_ns += tq - tp; tp = tq; }
         const double alpha_ = rho_ / v1[0];
         // E: s = r - alpha q ; <s,s> ; xin = c .* s
         double v2[1] = {0.0};
-        for (int64_t n = rb + tid; n < re; n += nth) {
-            const double sn = a.r[n] - alpha_ * a.q[n];
-            a.s[n] = sn;
-            v2[0] += sn * sn;
-            store_all_ranks(env, 0, n, a.c[n] * sn);
+        for (int64_t n0 = rb + tid; n0 < re; n0 += VU * nth) {
+            double rv[VU], qv[VU], cv[VU];
+#pragma unroll
+            for (int u = 0; u < VU; ++u) {
+                const int64_t n = n0 + u * nth;
+                if (n < re) { rv[u] = a.r[n]; qv[u] = a.q[n]; cv[u] = a.c[n]; }
+            }
+#pragma unroll
+            for (int u = 0; u < VU; ++u) {
+                const int64_t n = n0 + u * nth;
+                if (n < re) {
+                    const double sn = rv[u] - alpha_ * qv[u];
+                    a.s[n] = sn;
+                    v2[0] += sn * sn;
+                    store_all_ranks(env, 0, n, cv[u] * sn);
+                }
+            }
         }
         if (!grid_allreduce<1, false>(grid, env, epoch, SET_E, v2, smem)) return false;
+        if (clk) { tq = gtimer(); env.status->t_vec_ns[1] += tq - tp; }
         const bool exit_early = v2[0] < atol2;
         // F: t = J s ; <t,s>, <t,t>
         double v3[2] = {0.0, 0.0};
@@ -442,26 +501,40 @@ __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &
                 v3[1] += tn * tn;
             })) return false;
         if (!grid_allreduce<2, false>(grid, env, epoch, SET_F, v3, smem)) return false;
+        if (clk) tp = gtimer();
         const double omega_ = v3[0] / v3[1];
         matvecs += 2;
         // G: x, r updates ; <r,r>, <rhat,r>
         double v4[2] = {0.0, 0.0};
-        for (int64_t n = rb + tid; n < re; n += nth) {
-            const double pn = a.p[n], sn = a.s[n];
-            double xn, rn;
-            if (exit_early) {
-                xn = a.x[n] + alpha_ * pn;
-                rn = sn;
-            } else {
-                xn = a.x[n] + (alpha_ * pn + omega_ * sn);
-                rn = sn - omega_ * a.t[n];
+        for (int64_t n0 = rb + tid; n0 < re; n0 += VU * nth) {
+            double pv[VU], sv[VU], xv[VU], tv[VU], hv[VU];
+#pragma unroll
+            for (int u = 0; u < VU; ++u) {
+                const int64_t n = n0 + u * nth;
+                if (n < re) { pv[u] = a.p[n]; sv[u] = a.s[n]; xv[u] = a.x[n]; tv[u] = a.t[n]; hv[u] = a.rhat[n]; }
             }
-            a.x[n] = xn;
-            a.r[n] = rn;
-            v4[0] += rn * rn;
-            v4[1] += a.rhat[n] * rn;
+#pragma unroll
+            for (int u = 0; u < VU; ++u) {
+                const int64_t n = n0 + u * nth;
+                if (n < re) {
+                    const double pn = pv[u], sn = sv[u];
+                    double xn, rn;
+                    if (exit_early) {
+                        xn = xv[u] + alpha_ * pn;
+                        rn = sn;
+                    } else {
+                        xn = xv[u] + (alpha_ * pn + omega_ * sn);
+                        rn = sn - omega_ * tv[u];
+                    }
+                    a.x[n] = xn;
+                    a.r[n] = rn;
+                    v4[0] += rn * rn;
+                    v4[1] += hv[u] * rn;
+                }
+            }
         }
         if (!grid_allreduce<2, false>(grid, env, epoch, SET_G, v4, smem)) return false;
+        if (clk) { tq = gtimer(); env.status->t_vec_ns[2] += tq - tp; }
         rs = v4[0];
         rho_next = v4[1];
         long long k_ = (omega_ == 0.0 || alpha_ == 0.0) ? -11 : k + 1;

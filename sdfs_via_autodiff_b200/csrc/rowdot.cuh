@@ -1030,5 +1030,5 @@ static_assert(KRON_NMAX_LIMIT == 64, "the restricted-output contraction stages 8
 // their code size (instruction-cache footprint, compile time) bounded.
 static __device__ __noinline__ void kron_mode_store(const KronView &kv, int m, const double *in, double *out, double *smat,
                                                     double *stage) {
-    kron_mode_apply<false, false, true>(kv, m, in, smat, [&](int64_t idx, double s) { out[idx] = s; }, KronShare(stage));
+    kron_mode_apply<true, false, true>(kv, m, in, smat, [&](int64_t idx, double s) { out[idx] = s; }, KronShare(stage));   // exact tile counts: one copy
 }

@@ -4,9 +4,11 @@
 // global-memory round trip, no host involvement.  Same arithmetic and stopping rule as
 // k_sa_loop (successive_approx, solvers.py:19-48).
 #include "common.cuh"
+#include "rowdot.cuh"
 
 #include <stdlib.h>
 #define SMALL_MAX_N 160
+#define TRY_RC(x) do { int _rc = (x); if (_rc != SDFS_OK) return _rc; } while (0)
 
 struct SmallArgs {
     const double *P; int64_t ld; int N;
@@ -190,10 +192,166 @@ __global__ void __launch_bounds__(512, 1) k_sa_small_reg(SmallArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// Mid-size grids in factor form (the reference's default GCY grid, N = 3^6 = 729, lives here): the whole
+// state vector AND every factor matrix stay in the shared memory of ONE CTA for the whole solve.  An
+// iteration is D mode contractions between two shared-memory vectors (thread per output element, the
+// element -> (matrix row, fibre base) maps decoded once before the loop), the epilogue fused with the next
+// iteration's prologue, and a block-wide sup-norm: D + 2 __syncthreads per iteration instead of one grid
+// barrier per mode (k_sa_loop<KronLoopOp> costs 25-50 us per iteration on these grids, all of it barrier and
+// staging latency).  Same stopping rule as successive_approx (solvers.py:19-48): the error is taken before
+// the update is accepted.
+// ---------------------------------------------------------------------------
+#define KSMALL_THREADS 512
+struct KronSmallArgs {
+    const double *w_init; double *w_out;
+    double *wbuf;                  // 2 x ldn doubles of global scratch: ping-pong iterates (stay in L1/L2)
+    int *tab;                      // [n_modes][2][ldn] ints of global scratch: fibre base, matrix-row offset per element
+    long long ldn;
+    int poff[SDFS_MAX_DIMS];       // offset of each mode's matrices in the shared-memory pool
+    double tol; long long max_iter;
+    double *err_hist; long long hist_stride, hist_cap;
+    long long *iters_out; double *final_err_out;
+};
+
+__global__ void __launch_bounds__(KSMALL_THREADS, 1)
+k_sa_kron_small(const __grid_constant__ KronView kv, const __grid_constant__ KronSmallArgs a) {
+    extern __shared__ __align__(16) double ksm[];
+    __shared__ double s_red[KSMALL_THREADS / 32];
+    const int N = (int)kv.N;
+    const int ldn = (int)a.ldn;
+    double *va = ksm, *vb = ksm + ldn, *pool = ksm + 2 * ldn;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double theta = kv.theta, beta = kv.beta, inv_theta = 1.0 / kv.theta;
+    double *w_prev = a.wbuf, *w_next = a.wbuf + a.ldn;
+    // factor matrices -> shared memory (contiguous [n_mats][n][n] per mode)
+    for (int m = 0; m < kv.n_modes; ++m) {
+        const KronMode &md = kv.modes[m];
+        const int n = kv.shape[md.dim];
+        const int cnt = (int)md.Mcount * n * n;
+        for (int e = tid; e < cnt; e += KSMALL_THREADS) pool[a.poff[m] + e] = md.mat[e];
+    }
+    // element maps, once: for output element idx of mode m, the base of its fibre and its matrix row
+    for (int idx = tid; idx < N; idx += KSMALL_THREADS) {
+        int c[SDFS_MAX_DIMS], rem = idx;
+        for (int d = kv.D - 1; d >= 0; --d) { c[d] = rem % kv.shape[d]; rem /= kv.shape[d]; }
+        for (int m = 0; m < kv.n_modes; ++m) {
+            const KronMode &md = kv.modes[m];
+            const int n = kv.shape[md.dim];
+            int mat = 0;
+            for (int d = 0; d < kv.D; ++d) mat += c[d] * md.mstride[d];
+            a.tab[(2 * m) * ldn + idx] = idx - c[md.dim] * (int)md.stride;
+            a.tab[(2 * m + 1) * ldn + idx] = a.poff[m] + (mat * n + c[md.dim]) * n;
+        }
+        const double w0 = a.w_init[idx];
+        w_prev[idx] = w0;
+        va[idx] = kv.a_col[idx] * pow_pos(w0, theta);
+    }
+    __syncthreads();
+    long long it = 0;
+    double error = a.tol + 1.0;
+    double *in = va, *out = vb;
+    while (error > a.tol && it < a.max_iter) {
+        for (int m = 0; m < kv.n_modes; ++m) {
+            const int n = kv.shape[kv.modes[m].dim];
+            const int stride = (int)kv.modes[m].stride;
+            const int *tb = a.tab + (2 * m) * ldn, *tr = tb + ldn;
+            for (int i0 = tid; i0 < N; i0 += 2 * KSMALL_THREADS) {           // two outputs per trip: independent FMA chains
+                const int i1 = i0 + KSMALL_THREADS;
+                const bool v1 = i1 < N;
+                const double *ra = pool + tr[i0], *xa = in + tb[i0];
+                const double *rb = pool + (v1 ? tr[i1] : tr[i0]), *xb = in + (v1 ? tb[i1] : tb[i0]);
+                double sa0 = 0.0, sa1 = 0.0, sb0 = 0.0, sb1 = 0.0;
+                int j = 0;
+                for (; j + 1 < n; j += 2) {
+                    sa0 = fma(ra[j], xa[j * stride], sa0);
+                    sa1 = fma(ra[j + 1], xa[(j + 1) * stride], sa1);
+                    sb0 = fma(rb[j], xb[j * stride], sb0);
+                    sb1 = fma(rb[j + 1], xb[(j + 1) * stride], sb1);
+                }
+                if (j < n) { sa0 = fma(ra[j], xa[j * stride], sa0); sb0 = fma(rb[j], xb[j * stride], sb0); }
+                out[i0] = sa0 + sa1;
+                if (v1) out[i1] = sb0 + sb1;
+            }
+            __syncthreads();
+            double *t = in; in = out; out = t;
+        }
+        // epilogue + next prologue on the finished contraction (in), element by element in place
+        double e = 0.0;
+        for (int n0 = tid; n0 < N; n0 += 2 * KSMALL_THREADS) {              // two independent log/exp chains per trip
+            const int n1 = n0 + KSMALL_THREADS;
+            const bool v1 = n1 < N;
+            const double sa = kv.a_row[n0] * in[n0], sb = v1 ? kv.a_row[n1] * in[n1] : 1.0;
+            const double ya = 1.0 + beta * pow_pos(sa, inv_theta), yb = 1.0 + beta * pow_pos(sb, inv_theta);
+            const double xa = kv.a_col[n0] * pow_pos(ya, theta), xb = v1 ? kv.a_col[n1] * pow_pos(yb, theta) : 0.0;
+            e = nanmax(e, fabs(ya - w_prev[n0]));
+            w_next[n0] = ya;
+            in[n0] = xa;
+            if (v1) {
+                e = nanmax(e, fabs(yb - w_prev[n1]));
+                w_next[n1] = yb;
+                in[n1] = xb;
+            }
+        }
+        e = warp_nanmax(e);
+        if (lane == 0) s_red[warp] = e;
+        __syncthreads();
+        double mx = s_red[0];
+#pragma unroll
+        for (int w = 1; w < KSMALL_THREADS / 32; ++w) mx = nanmax(mx, s_red[w]);
+        error = mx;
+        __syncthreads();                           // s_red is rewritten next iteration; the staged vector is complete
+        if (tid == 0 && a.err_hist && (it % a.hist_stride) == 0 && (it / a.hist_stride) < a.hist_cap)
+            a.err_hist[it / a.hist_stride] = error;
+        double *t = w_prev; w_prev = w_next; w_next = t;
+        ++it;
+    }
+    for (int n = tid; n < N; n += KSMALL_THREADS) a.w_out[n] = w_prev[n];
+    if (tid == 0) {
+        *a.iters_out = it;
+        *a.final_err_out = error;
+    }
+}
+
+static int small_sa_kron_try(sdfs_op *op, const double *d_w_init, double tol, int64_t max_iter, double *d_w_out,
+                             double *d_err_hist, int64_t hist_stride, int64_t hist_cap) {
+    sdfs_ctx *ctx = op->ctx;
+    const KronView &kv = op->kv;
+    static const long long max_n = getenv("SDFS_SMALL_KRON_MAX") ? atoll(getenv("SDFS_SMALL_KRON_MAX")) : 8192;
+    if (kv.N > max_n || op->kron_sharded) return 0;
+    KronSmallArgs a{};
+    long long pool = 0;
+    for (int m = 0; m < kv.n_modes; ++m) {
+        const int n = kv.shape[kv.modes[m].dim];
+        a.poff[m] = (int)pool;
+        pool += kv.modes[m].Mcount * n * n;
+    }
+    const long long ldn = (kv.N + 1) & ~1LL;
+    const size_t smem = (size_t)(2 * ldn + pool) * sizeof(double);
+    if (smem > 200 * 1024) return 0;
+    // global scratch from the work vectors: 2 iterates + 2 int tables per mode (one double holds two ints)
+    TRY_RC(op_ensure_work(op, 16));
+    if (ldn > op->ldv || 2 + kv.n_modes > 16) return 0;
+    a.w_init = d_w_init; a.w_out = d_w_out;
+    a.wbuf = op->work; a.ldn = ldn;
+    a.tab = (int *)(op->work + 2 * op->ldv);
+    a.tol = tol; a.max_iter = max_iter; a.err_hist = d_err_hist;
+    a.hist_stride = hist_stride > 0 ? hist_stride : 1; a.hist_cap = d_err_hist ? hist_cap : 0;
+    a.iters_out = (long long *)ctx->d_status;
+    a.final_err_out = (double *)((char *)ctx->d_status + 32);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_sa_kron_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sa_kron_small<<<1, KSMALL_THREADS, smem, ctx->stream>>>(kv, a);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 1;
+}
+
 // returns 1 if the small path handled the solve, 0 if not applicable, <0 on error
 int small_sa_try(sdfs_op *op, const double *d_w_init, double tol, int64_t max_iter, double *d_w_out,
                  double *d_err_hist, int64_t hist_stride, int64_t hist_cap) {
     sdfs_ctx *ctx = op->ctx;
+    if (op->storage == SDFS_STORAGE_KRON)
+        return small_sa_kron_try(op, d_w_init, tol, max_iter, d_w_out, d_err_hist, hist_stride, hist_cap);
     if (op->storage != SDFS_STORAGE_DENSE) return 0;
     const DenseView &dv = op->dv;
     if (dv.row_begin != 0 || dv.row_end != dv.N) return 0;

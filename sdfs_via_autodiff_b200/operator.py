@@ -109,7 +109,10 @@ class WCOperator:
         ctx = factors.ctx
         N = int(np.prod(factors.shapes))
         if storage == "auto":
-            storage = "dense" if N <= 32768 else "kron"
+            # up to 160 states the dense P lives in the registers / shared memory of one CTA (1.3 us per SA
+            # iteration); above that the factor form is faster everywhere (3x at 10^4 states, and dense P is
+            # impossible beyond ~1.5 10^5), so "auto" never materialises a large P - ask for "dense" to get one
+            storage = "dense" if N <= 160 else "kron"
         st = {"dense": STORAGE_DENSE, "kron": STORAGE_KRON, "kron_local": STORAGE_KRON_LOCAL}[storage]
         h = C.c_void_p()
         check(lib.sdfs_op_from_factors(ctx.handle, factors.handle, st, C.byref(h)), ctx.handle)

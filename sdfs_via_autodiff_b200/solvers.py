@@ -96,6 +96,8 @@ def newton_solver(f, x_init, tol=default_tolerance, max_iter=default_max_iter,
                                 C.byref(ferr), h_err, h_inner, cap, C.byref(nmv)), ctx.handle)
     k = outer.value
     _report(list(h_err[:min(k, cap)]) if verbose else None, k, max_iter, verbose, print_skip, stride=1)
+    if verbose and k > cap:
+        print(f"(error history is recorded for the first {cap} outer iterations only)")
     if return_info:
         n = min(k, cap)
         return w_out, k, dict(final_error=ferr.value, errors=list(h_err[:n]),

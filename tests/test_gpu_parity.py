@@ -200,6 +200,52 @@ def test_successive_approx_edge_semantics():
         op(np.ones(7))
 
 
+@pytest.mark.parametrize("model,shapes", [("gcy", (3,) * 6), ("ssy", (6, 6, 6, 6)), ("ssy", (3, 4, 17, 5)),
+                                          ("ssy", (10, 10, 10, 10))])
+def test_successive_approx_factor_form_mid_size_grids(model, shapes, capsys):
+    """Factor-form SA below 8 192 states runs as ONE CTA with the vector and every factor matrix resident in
+    shared memory (k_sa_kron_small; the reference's default GCY grid (3,)^6 is one of these), above that in the
+    cooperative loop kernel: both reproduce the oracle's iteration counts, fixed points, printed trace and
+    the reference's edge semantics (solvers.py:19-48)."""
+    if model == "gcy":
+        ref = O.GCY()
+        kop = O.KronGCY(shapes, ref.params, O.discretize_gcy(ref, shapes))
+        op = S.make_T_gcy(S.GCY(), shapes, storage="kron")
+    else:
+        ref = O.SSY()
+        kop = O.KronSSY(shapes, ref.params, O.discretize_ssy(ref, shapes))
+        op = S.make_T_ssy(S.SSY(), shapes, storage="kron")
+    w0 = np.full(shapes, 800.0)
+    w_ref, k_ref = O.successive_approx(kop.T, w0, verbose=False)
+    capsys.readouterr()
+    w, k = S.successive_approx(op, w0, print_skip=1000)
+    out = capsys.readouterr().out
+    assert k == k_ref
+    np.testing.assert_allclose(np.asarray(w), w_ref, rtol=RTOL_W)
+    pairs, rest = _trace(out)
+    assert [p[0] for p in pairs] == list(range(0, k, 1000)) and f"Iteration converged after {k} iterations" in rest
+    # the printed errors are the oracle's sup-norms at those iterations
+    errs = []
+    x = w0
+    for i in range(1001):
+        y = kop.T(x)
+        if i % 1000 == 0:
+            errs.append(np.max(np.abs(y - x)))
+        x = y
+    np.testing.assert_allclose([p[1] for p in pairs[:2]], errs, rtol=1e-9)
+    # max_iter, NaN and zero-iteration semantics
+    w5, k5 = S.successive_approx(op, w0, tol=0.0, max_iter=5, verbose=False)
+    x = w0
+    for _ in range(5):
+        x = kop.T(x)
+    assert k5 == 5
+    np.testing.assert_allclose(np.asarray(w5), x, rtol=1e-12)
+    wn, kn = S.successive_approx(op, np.full(shapes, -1.0), verbose=False)
+    assert kn == 1 and np.isnan(np.asarray(wn)).all()
+    wz, kz = S.successive_approx(op, w0, max_iter=0, verbose=False)
+    assert kz == 0 and (np.asarray(wz) == 800.0).all()
+
+
 def _trace(out):
     """(iteration, error) pairs and the remaining lines of a solver's stdout."""
     pairs, rest = [], []
