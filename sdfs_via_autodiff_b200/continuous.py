@@ -164,6 +164,48 @@ def wc_ratio_continuous(model, *grid_sizes, num_std_devs=3.2, d=5, mc_draw_size=
     return grids, w_star
 
 
+def compare_T_factories(T_fact_old, T_fact_new, shape=(5, 6, 7, 8), seed=1234, n=100):
+    """Compare the results and speed of two function factories for T (ssy_wc_ratio_continuous.py:330-452):
+    both are called as ``fact(params_quad, 'quadrature', batch_size)`` on the reference's test set-up (SSY,
+    3 standard deviations, 4 quadrature nodes per dimension), applied to ``n`` random w, and one Newton step
+    of each is compared as well.  Prints the reference's report lines and returns True when both agree."""
+    import time
+    from .ssy_model import SSY
+    from .solvers import newton_solver
+    ssy = SSY()
+    grids = build_grid(ssy, *shape, num_std_devs=3.0)
+    nodes, weights = gauss_hermite_normal(4, len(grids))
+    params_quad = (ssy.params, grids, nodes, weights)
+    batch_size = int(np.prod(shape))
+    T_old = T_fact_old(params_quad, "quadrature", batch_size)
+    T_new = T_fact_new(params_quad, "quadrature", batch_size)
+    ctx = T_new.ctx if hasattr(T_new, "ctx") else Context.default()
+    print("----- Testing the Operator T -----")
+    w0 = np.zeros(shape) + 1.0
+    t0 = time.time(); T_old(w0); ctx.sync(); t1 = time.time(); T_new(w0); ctx.sync(); t2 = time.time()
+    print("Compilation time: {:.4f}ms vs {:.4f}ms".format((t1 - t0) * 1000, (t2 - t1) * 1000))
+    w0_array = np.random.default_rng(seed).uniform(size=(n,) + tuple(shape)) + 0.5
+    t0 = time.time()
+    old = [np.asarray(T_old(w0_array[i])) for i in range(n)]
+    t1 = time.time()
+    new = [np.asarray(T_new(w0_array[i])) for i in range(n)]
+    t2 = time.time()
+    same_T = all(np.allclose(a, b) for a, b in zip(old, new))
+    print("Speed comparison for {} runs: {:.4f}ms vs {:.4f}ms".format(n, 1000 * (t1 - t0), 1000 * (t2 - t1)))
+    print("Same results? {}".format(same_T))
+    print("\n----- Testing Newton's Method -----")
+    m = max(1, int(n / 50))
+    t0 = time.time()
+    old = [np.asarray(newton_solver(T_old, 400.0 * w0_array[i], max_iter=1, verbose=False)[0]) for i in range(m)]
+    t1 = time.time()
+    new = [np.asarray(newton_solver(T_new, 400.0 * w0_array[i], max_iter=1, verbose=False)[0]) for i in range(m)]
+    t2 = time.time()
+    print("Speed comparison for {} runs: {:.4f}s vs {:.4f}s".format(m, t1 - t0, t2 - t1))
+    same_N = all(np.allclose(a, b) for a, b in zip(old, new))
+    print("Same results? {}".format(same_N))
+    return same_T and same_N
+
+
 def save_wstar(filename, grids, w_star):
     """The reference's on-disk format (ssy_wc_ratio_continuous.py:291-295): two consecutive
     np.save records in one file, the grids then w_star."""

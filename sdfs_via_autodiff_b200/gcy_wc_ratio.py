@@ -31,6 +31,28 @@ def T_gcy(w, shapes, params, arrays, storage="auto"):
     return op(w)
 
 
+def T_gcy_loops(w, shapes, params, arrays):
+    """Counterpart of the reference's loop form (gcy_wc_ratio.py:244-302): T from the explicit single-index
+    transition matrix (dense-storage operator), independent of the sum-factorised ``T_gcy``."""
+    return cached_operator(MODEL_GCY, shapes, params, arrays, "dense")(w)
+
+
+def test_vectorized_equals_loops(shapes=(2, 3, 4, 5, 6, 7)):
+    """gcy_wc_ratio.py:305-316: the factor-form T and the explicit-matrix T agree at a random w."""
+    gcy = GCY()
+    params = gcy.params
+    arrays = discretize_gcy(gcy, shapes)
+    w = np.exp(np.random.randn(*shapes))  # Test operator at w
+    w1 = T_gcy(w, shapes, params, arrays, storage="kron")
+    w2 = T_gcy_loops(w, shapes, params, arrays)
+    same = bool(np.allclose(np.asarray(w1), np.asarray(w2)))
+    print(same)
+    return same
+
+
+test_vectorized_equals_loops.__test__ = False   # a driver, not a pytest test
+
+
 def test_compute_wc_ratio_gcy(shapes=(3, 3, 3, 3, 3, 3), algo="successive_approx"):
     """Solve a small version of the model using T_gcy."""
     gcy = GCY()

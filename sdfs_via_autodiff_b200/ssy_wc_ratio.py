@@ -35,6 +35,29 @@ def T_ssy(w, shapes, params, arrays, storage="auto"):
     return op(w)
 
 
+def T_ssy_loops(w, shapes, params, arrays):
+    """Counterpart of the reference's loop form (ssy_wc_ratio.py:159-199): T evaluated from the explicit
+    single-index transition matrix P (one row-times-vector reduction per state, temp_ssy.py:106), i.e. the
+    dense-storage operator - an implementation independent of the sum-factorised one behind ``T_ssy``."""
+    return cached_operator(MODEL_SSY, shapes, params, arrays, "dense")(w)
+
+
+def test_vectorized_equals_loops(shapes=(4, 7, 6, 5)):
+    """ssy_wc_ratio.py:202-213: the factor-form T and the explicit-matrix T agree at a random w."""
+    ssy = SSY()
+    params = ssy.params
+    arrays = discretize_ssy(ssy, shapes)
+    w = np.exp(np.random.randn(*shapes))  # Test operator at w
+    w1 = T_ssy(w, shapes, params, arrays, storage="kron")
+    w2 = T_ssy_loops(w, shapes, params, arrays)
+    same = bool(np.allclose(np.asarray(w1), np.asarray(w2)))
+    print(same)
+    return same
+
+
+test_vectorized_equals_loops.__test__ = False   # a driver, not a pytest test
+
+
 def test_compute_wc_ratio_ssy(shapes=(2, 3, 4, 5), algo="successive_approx"):
     """Solve a small version of the model using T_ssy."""
     ssy = SSY()

@@ -31,6 +31,6 @@ def test_row_sharded_operator_and_fused_loops_two_ranks(fused):
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(ROOT, "tools", "mgpu_check.py")],
                        capture_output=True, text=True, timeout=600, cwd=ROOT,
-                       env=dict(os.environ, SDFS_FUSED_EXCHANGE=fused))
+                       env=dict(os.environ, SDFS_FUSED_EXCHANGE=fused, SDFS_KRON_SHARD_MIN="0"))   # shard the small test grids too
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "ALL PASS" in r.stdout and "FAIL" not in r.stdout, r.stdout[-3000:]

@@ -541,6 +541,64 @@ def test_anderson_solver_device(storage, capsys):
     assert k3 == 13 and "Warning: Hit maximum iteration number 13" in capsys.readouterr().out
 
 
+def test_anderson_update_rule_step_by_step_on_an_affine_map():
+    """f1: the Anderson update the device loop implements, iterate by iterate, against a hand derivation.
+
+    With theta = 1 the operator is the affine map f(x) = 1 + beta P x (2 x 2 here).  For history size m = 2
+    the constrained least-squares weights have the closed form
+        alpha_1 = (G22 + rho - G12) / (G11 + G22 + 2 rho - 2 G12),  alpha_2 = 1 - alpha_1,   G_ij = <r_i, r_j>,
+    (the minimiser of alpha^T (G + rho I) alpha subject to alpha_1 + alpha_2 = 1 -- the bordered system
+    [[0, 1^T], [1, G + rho I]] [nu; alpha] = e_0 of jaxopt's anderson.py), and the update is
+        x+ = sum_i alpha_i (x_i + beta_mix r_i)   once k >= m and k % mixing_frequency == 0,   x+ = f(x) otherwise,
+    with the history slots filled round-robin (slot k mod m), initial history = x0 tiled, residuals zero.
+    jaxopt itself is not installable here (parity with it stays unpinned); this pins the device arithmetic to
+    the rule stated in oracle/solvers.py::anderson_solver and in the header."""
+    import ctypes as C
+    from sdfs_via_autodiff_b200._lib import lib, check
+    P = np.array([[0.6, 0.4], [0.3, 0.7]])
+    β_op = 0.9
+    f = lambda x: 1 + β_op * (P @ x)
+    op = S.WCOperator.from_dense(P, np.ones(2), np.ones(2), β_op, 1.0)
+    x0 = np.array([3.0, -1.0])
+    m, mix, β_mix, ρ = 2, 1, 0.5, 1e-6
+
+    def by_hand(K):
+        X = [x0.copy(), x0.copy()]
+        R = [np.zeros(2), np.zeros(2)]
+        x = x0.copy()
+        for k in range(K):
+            pos = k % m
+            r = f(x) - x
+            X[pos], R[pos] = x.copy(), r
+            if k >= m and k % mix == 0:
+                G11, G22, G12 = R[0] @ R[0], R[1] @ R[1], R[0] @ R[1]
+                a1 = (G22 + ρ - G12) / (G11 + G22 + 2 * ρ - 2 * G12)
+                a2 = 1 - a1
+                x = a1 * (X[0] + β_mix * R[0]) + a2 * (X[1] + β_mix * R[1])
+            else:
+                x = x + r
+        return x
+
+    ctx = op.ctx
+    for K in range(0, 9):
+        w_out = ctx.empty((2,))
+        iters, ferr = C.c_int64(), C.c_double()
+        check(lib.sdfs_solve_anderson(op.handle, ctx.asarray(x0).ptr, 0.0, K, m, mix, β_mix, ρ, w_out.ptr,
+                                      C.byref(iters), C.byref(ferr)), ctx.handle)
+        assert iters.value == K
+        np.testing.assert_allclose(np.asarray(w_out), by_hand(K), rtol=1e-11, atol=1e-13)
+        # the oracle's general-m implementation (linear solve of the bordered system) agrees with the closed form
+        w_o, k_o = O.anderson_solver(f, x0, tol=0.0, max_iter=K, verbose=False, history_size=m, mixing_frequency=mix,
+                                     beta=β_mix, ridge=ρ)
+        np.testing.assert_allclose(w_o, by_hand(K), rtol=1e-10, atol=1e-12)
+    # and the accelerated iteration reaches the fixed point (I - beta P) x = 1
+    x_star = np.linalg.solve(np.eye(2) - β_op * P, np.ones(2))
+    w_out = ctx.empty((2,))
+    check(lib.sdfs_solve_anderson(op.handle, ctx.asarray(x0).ptr, 1e-12, 200, m, mix, β_mix, ρ, w_out.ptr, C.byref(iters),
+                                  C.byref(ferr)), ctx.handle)
+    np.testing.assert_allclose(np.asarray(w_out), x_star, rtol=1e-9)
+
+
 def test_loglinear_guess_on_device_and_warm_start():
     from oracle.loglinear import loglinear_grid_ssy, loglinear_grid_gcy
     shapes = (4, 5, 6, 7)
@@ -641,6 +699,35 @@ def test_continuous_state_operators():
         np.testing.assert_allclose(np.asarray(f_disk(pts)), ref_interp(pts, np.asarray(w2), g2), rtol=1e-13)
     f_mem = S.construct_wstar_callable(w2, g2)
     np.testing.assert_allclose(np.asarray(f_mem(pts)), ref_interp(pts, np.asarray(w2), g2), rtol=1e-13)
+
+
+def test_reference_side_test_drivers(capsys):
+    """Product-side counterparts of the reference's own check functions: test_vectorized_equals_loops
+    (ssy_wc_ratio.py:202-213, gcy_wc_ratio.py:305-316: factor form against the explicit-matrix form) and
+    compare_T_factories (ssy_wc_ratio_continuous.py:330-452)."""
+    from sdfs_via_autodiff_b200 import ssy_wc_ratio, gcy_wc_ratio
+    assert ssy_wc_ratio.test_vectorized_equals_loops() is True
+    assert gcy_wc_ratio.test_vectorized_equals_loops(shapes=(2, 3, 4, 3, 2, 3)) is True
+    assert capsys.readouterr().out.split() == ["True", "True"]
+    z = np.exp(np.random.default_rng(5).standard_normal((2, 3, 4, 5)))
+    arrays = S.discretize_ssy(S.SSY(), (2, 3, 4, 5))
+    np.testing.assert_allclose(np.asarray(S.T_ssy_loops(z, (2, 3, 4, 5), S.SSY().params, arrays)),
+                               O.T_ssy_loops(z, (2, 3, 4, 5), O.SSY().params, arrays), rtol=RTOL_T)
+    assert S.compare_T_factories(S.T_fun_factory, S.T_fun_factory, shape=(4, 5, 4, 6), n=50) is True
+    out = capsys.readouterr().out
+    assert "----- Testing the Operator T -----" in out and out.count("Same results? True") == 2
+
+
+def test_device_interpolation_matches_reference_run_vectors(golden_dir):
+    """f2/f4 pin: sdfs_interp_points (lin_interp, construct_wstar_callable) against outputs of the reference's
+    own utils.py:6-23 executed from source (tests/golden/make_golden_interp.py -> lin_interp.npz)."""
+    z = np.load(os.path.join(golden_dir, "lin_interp.npz"))
+    for tag in ("d4", "d6"):
+        grids = [z[f"{tag}_grid{i}"] for i in range(len(z[f"{tag}_sizes"]))]
+        got = np.asarray(S.lin_interp(z[f"{tag}_x"], z[f"{tag}_vals"], grids))
+        np.testing.assert_allclose(got, z[f"{tag}_y_ref"], rtol=1e-13)
+        f = S.construct_wstar_callable(z[f"{tag}_vals"], grids)
+        np.testing.assert_allclose(np.asarray(f(z[f"{tag}_x"])), z[f"{tag}_y_ref"], rtol=1e-13)
 
 
 def test_error_behaviour_and_pinned_buffers():

@@ -301,3 +301,15 @@ def test_continuous_oracle_consistency():
     draws = rng.standard_normal((4, 20000))
     mc = ContSSY(O.SSY(), sizes, draws, np.full(20000, 1 / 20000))
     np.testing.assert_allclose(mc.T(ws), ContSSY(O.SSY(), sizes, n5.T, w5).T(ws), rtol=1e-2)
+
+
+def test_interpolation_oracle_matches_reference_run_vectors(golden_dir):
+    """utils.py:6-23 (vals_to_coords + map_coordinates(order=1, mode='nearest')) executed from the reference
+    source (tests/golden/make_golden_interp.py): the oracle's multilinear interpolation reproduces it, inside the
+    grid, on nodes and outside (nearest-edge extension), in 4 and 6 dimensions."""
+    from oracle.continuous import lin_interp
+    z = np.load(os.path.join(golden_dir, "lin_interp.npz"))
+    for tag in ("d4", "d6"):
+        grids = [z[f"{tag}_grid{i}"] for i in range(len(z[f"{tag}_sizes"]))]
+        got = lin_interp(z[f"{tag}_x"], z[f"{tag}_vals"], grids)
+        np.testing.assert_allclose(got, z[f"{tag}_y_ref"], rtol=1e-13)

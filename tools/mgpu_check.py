@@ -2,6 +2,7 @@
 row-sharded dense operator vs the oracle; NCCL all-gather path for single applications,
 fused peer-store path for the device-resident SA / Newton loops."""
 import os, sys, time
+os.environ.setdefault("SDFS_KRON_SHARD_MIN", "0")      # the small test grids are slab-sharded too (default: >= 4 M states)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch.distributed as dist
