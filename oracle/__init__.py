@@ -18,9 +18,14 @@ Pinning status (see DESIGN.md "Oracle"):
     (code/ssy/discrete/sandpit.ipynb), reproduced to 3-7 digits; the
     third-party algorithms (quantecon.rouwenhorst, jax bicgstab) are restated
     from their published form because neither library is installable here.
-  * converged w*, iteration counts, GCY solutions, SDF: parity unpinned
-    (self-pinned by this oracle; the SDF has no reference code at all and is
-    checked through the Euler identity E[M R_w] = 1).
+  * interpolation of the continuous-state rows (utils.py:6-23): PINNED against the reference's own
+    functions executed from source (tests/golden/make_golden_interp.py -> lin_interp.npz).
+  * SDF: the reference has no SDF code.  The closed forms (e_sdf, q_f, M-bar) are PINNED to an
+    independent Gauss-Hermite integration of the paper's un-integrated log M' (oracle/sdf.py::
+    sdf_quadrature, paper/autosdfs.tex:374-384), including the pricing identity E[M' R_w'] = 1 at the
+    fixed point of the reference-pinned T; a wrong sign or a missing 1/2 fails the check.
+  * converged w*, iteration counts, GCY solutions, Anderson vs jaxopt, Monte-Carlo draws: parity
+    unpinned (self-pinned by this oracle).
 """
 from .models import SSY, GCY                                    # noqa: F401
 from .rouwenhorst import rouwenhorst                            # noqa: F401

@@ -30,6 +30,7 @@ int small_sa_try(sdfs_op *op, const double *d_w_init, double tol, int64_t max_it
 
 #define HIST_CAP 120       // outer Newton iterations recorded in the status page
 #define VU 4               // elements per thread and trip in the Krylov vector phases
+#define VUC 8              // ... in the phases that read at most four vectors
 #define GMRES_MAX_RESTART 64
 #define GMRES_WS_BYTES (((GMRES_MAX_RESTART + 1) * 2 + GMRES_MAX_RESTART * 3 + GMRES_MAX_RESTART * GMRES_MAX_RESTART) * sizeof(double) + 16)
 
@@ -116,7 +117,7 @@ __device__ __forceinline__ void cta_sum(double (&v)[NV], double *smem /* >= SDFS
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             double s = 0.0;
-            for (int w = 0; w < SDFS_WARPS; ++w) s += smem[w * NV + j];
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += smem[w * NV + j];
             v[j] = s;
         }
 }
@@ -169,7 +170,7 @@ __device__ __forceinline__ bool grid_allreduce(cg::grid_group &grid, const LoopE
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 double s = 0.0;
-                for (int w = 0; w < SDFS_WARPS; ++w) s = nanmax(s, smem[w * NV + j]);
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s = nanmax(s, smem[w * NV + j]);
                 v[j] = s;
             }
     } else {
@@ -182,6 +183,8 @@ __device__ __forceinline__ bool grid_allreduce(cg::grid_group &grid, const LoopE
 }
 
 __device__ __forceinline__ void store_all_ranks(const LoopEnv &env, int buf, int64_t n, double val) {
+    if (env.nranks == 1) { env.xin[0][buf][n] = val; return; }      // single GPU: no loop, no pointer table walk
+#pragma unroll 1
     for (int r = 0; r < env.nranks; ++r) env.xin[r][buf][n] = val;
 }
 
@@ -196,6 +199,8 @@ struct Scratch {
 
 struct DenseLoopOp {
     static constexpr int kMinBlocks = 1;
+    static constexpr int kThreads = SDFS_THREADS;      // 8 consumer warps + the TMA producer warp
+    static constexpr bool kTwoStage = false;
     DenseView dv;
     __host__ __device__ size_t dyn_smem() const { return dv.vec2 ? sizeof(RowPipe<1>) : 0; }
     __device__ __forceinline__ void init(Scratch &sc) const {
@@ -231,10 +236,12 @@ struct DenseLoopOp {
 };
 
 struct KronLoopOp {
-    static constexpr int kMinBlocks = 2;     // <= 112 registers: two 288-thread CTAs (18 warps) per SM hide the fragment-load latency
+    static constexpr int kMinBlocks = 2;     // two CTAs per SM
+    static constexpr int kThreads = 256;     // 128 registers per thread: at 288 threads (<= 112, 96 in practice) the Krylov vector
+                                             // phases spilled their batched loads to local memory (STL/LDL in the SASS)
     KronView kv;
     double *tmp0, *tmp1;
-    __host__ __device__ size_t dyn_smem() const { return (KRON_SMAT_DOUBLES + SDFS_WARPS * KRON_STAGE_DOUBLES_PER_WARP) * sizeof(double); }
+    __host__ __device__ size_t dyn_smem() const { return (KRON_SMAT_DOUBLES + (kThreads / 32) * KRON_STAGE_DOUBLES_PER_WARP) * sizeof(double); }
     __device__ __forceinline__ void init(Scratch &) const {}
     __device__ __forceinline__ int64_t N() const { return kv.N; }
     __device__ __forceinline__ int64_t row_begin() const { return kv.row_begin; }     // slab of the leading axis (sharded view)
@@ -259,9 +266,8 @@ struct KronLoopOp {
     // round 1, the epilogue's scattered dependent loads - d, p, r-hat per output - made that mode cost 169 us
     // against 68 us for the others at 9.8 M states, and every call site carried its own copy of the
     // tensor-core code.)
-    template <class Epi>
-    __device__ __forceinline__ bool apply(cg::grid_group &grid, const LoopEnv &env, unsigned long long &epoch,
-                                          Scratch &sc, const double *xin, const double *, Epi &&epi) const {
+    static constexpr bool kTwoStage = true;      // contract() leaves P xin in a vector; callers may run their own vector phase on it
+    __device__ __forceinline__ const double *contract(cg::grid_group &grid, const LoopEnv &env, Scratch &sc, const double *xin) const {
         const double *in = xin;
         const bool clk = blockIdx.x == 0 && threadIdx.x == 0;
         unsigned long long t0 = 0, t1;
@@ -275,6 +281,16 @@ struct KronLoopOp {
             if (clk) { t1 = gtimer(); if (m < 4) env.status->t_mode_ns[m] += t1 - t0; t0 = t1; }
             in = out;
         }
+        if (clk) { env.status->t_apply_ns += t0 - tb; env.status->n_apply += 1; }
+        return in;
+    }
+    template <class Epi>
+    __device__ __forceinline__ bool apply(cg::grid_group &grid, const LoopEnv &env, unsigned long long &epoch,
+                                          Scratch &sc, const double *xin, const double *, Epi &&epi) const {
+        const double *in = contract(grid, env, sc, xin);
+        const bool clk = blockIdx.x == 0 && threadIdx.x == 0;
+        unsigned long long t0 = 0;
+        if (clk) t0 = gtimer();
         const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         const int64_t nth = (int64_t)gridDim.x * blockDim.x;
         const int64_t rb = kv.row_begin, re = kv.row_end;
@@ -291,8 +307,8 @@ struct KronLoopOp {
                 if (n < re) epi(n, sv[u]);
             }
         }
-        if (clk) { t1 = gtimer(); env.status->t_epi_ns += t1 - t0; env.status->t_apply_ns += t1 - tb; env.status->n_apply += 1; }
-        (void)env; (void)epoch;
+        if (clk) env.status->t_epi_ns += gtimer() - t0;
+        (void)epoch;
         return true;
     }
 };
@@ -301,6 +317,8 @@ struct KronLoopOp {
 // the full current w beside the vector it is applied to.
 struct ContLoopOp {
     static constexpr int kMinBlocks = 2;
+    static constexpr int kThreads = SDFS_THREADS;
+    static constexpr bool kTwoStage = false;
     static constexpr bool kNeedsW = true;
     ContView cv;
     __host__ __device__ size_t dyn_smem() const { return 0; }
@@ -341,7 +359,7 @@ struct SAArgs {
 };
 
 template <class Op>
-__global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_sa_loop(const __grid_constant__ Op op, SAArgs a, LoopEnv env) {
+__global__ void __launch_bounds__(Op::kThreads, Op::kMinBlocks) k_sa_loop(const __grid_constant__ Op op, const __grid_constant__ SAArgs a, const __grid_constant__ LoopEnv env) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ double smem[SDFS_WARPS * NVAL + NVAL];
@@ -438,15 +456,15 @@ __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &
         if (clk) tp = gtimer();
         // (vector phases: VU independent elements per trip, every load issued before the first store - one
         // element per trip left the loops latency-bound at ~half of HBM bandwidth with 18 warps per SM)
-        for (int64_t n0 = rb + tid; n0 < re; n0 += VU * nth) {
-            double rv[VU], pv[VU], qv[VU], cv[VU];
+        for (int64_t n0 = rb + tid; n0 < re; n0 += VUC * nth) {
+            double rv[VUC], pv[VUC], qv[VUC], cv[VUC];
 #pragma unroll
-            for (int u = 0; u < VU; ++u) {
+            for (int u = 0; u < VUC; ++u) {
                 const int64_t n = n0 + u * nth;
                 if (n < re) { rv[u] = a.r[n]; pv[u] = a.p[n]; qv[u] = a.q[n]; cv[u] = a.c[n]; }
             }
 #pragma unroll
-            for (int u = 0; u < VU; ++u) {
+            for (int u = 0; u < VUC; ++u) {
                 const int64_t n = n0 + u * nth;
                 if (n < re) {
                     const double pn = rv[u] + beta * (pv[u] - omega * qv[u]);
@@ -459,7 +477,29 @@ __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &
         if (clk) { tq = gtimer(); env.status->t_vec_ns[0] += tq - tp; }
         // D: q = J p = d .* P(c .* p) - p ; <rhat,q>
         double v1[1] = {0.0};
-        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], env.xin[env.rank][1], [&](int64_t n, double sum) {
+        if constexpr (Op::kTwoStage) {
+            const double *sum = op.contract(grid, env, sc, env.xin[env.rank][0]);
+            unsigned long long te = 0;
+            if (clk) te = gtimer();
+            for (int64_t n0 = rb + tid; n0 < re; n0 += VU * nth) {
+                double sv[VU], dv[VU], pv[VU], hv[VU];
+#pragma unroll
+                for (int u = 0; u < VU; ++u) {
+                    const int64_t n = n0 + u * nth;
+                    if (n < re) { sv[u] = sum[n]; dv[u] = a.d[n]; pv[u] = a.p[n]; hv[u] = a.rhat[n]; }
+                }
+#pragma unroll
+                for (int u = 0; u < VU; ++u) {
+                    const int64_t n = n0 + u * nth;
+                    if (n < re) {
+                        const double qn = dv[u] * sv[u] - pv[u];
+                        a.q[n] = qn;
+                        v1[0] += hv[u] * qn;
+                    }
+                }
+            }
+            if (clk) env.status->t_epi_ns += gtimer() - te;
+        } else if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], env.xin[env.rank][1], [&](int64_t n, double sum) {
                 const double qn = a.d[n] * sum - a.p[n];
                 a.q[n] = qn;
                 v1[0] += a.rhat[n] * qn;
@@ -470,15 +510,15 @@ __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &
         const double alpha_ = rho_ / v1[0];
         // E: s = r - alpha q ; <s,s> ; xin = c .* s
         double v2[1] = {0.0};
-        for (int64_t n0 = rb + tid; n0 < re; n0 += VU * nth) {
-            double rv[VU], qv[VU], cv[VU];
+        for (int64_t n0 = rb + tid; n0 < re; n0 += VUC * nth) {
+            double rv[VUC], qv[VUC], cv[VUC];
 #pragma unroll
-            for (int u = 0; u < VU; ++u) {
+            for (int u = 0; u < VUC; ++u) {
                 const int64_t n = n0 + u * nth;
                 if (n < re) { rv[u] = a.r[n]; qv[u] = a.q[n]; cv[u] = a.c[n]; }
             }
 #pragma unroll
-            for (int u = 0; u < VU; ++u) {
+            for (int u = 0; u < VUC; ++u) {
                 const int64_t n = n0 + u * nth;
                 if (n < re) {
                     const double sn = rv[u] - alpha_ * qv[u];
@@ -493,7 +533,30 @@ __device__ __forceinline__ bool bicgstab_device(cg::grid_group &grid, const Op &
         const bool exit_early = v2[0] < atol2;
         // F: t = J s ; <t,s>, <t,t>
         double v3[2] = {0.0, 0.0};
-        if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], env.xin[env.rank][1], [&](int64_t n, double sum) {
+        if constexpr (Op::kTwoStage) {
+            const double *sum = op.contract(grid, env, sc, env.xin[env.rank][0]);
+            unsigned long long te = 0;
+            if (clk) te = gtimer();
+            for (int64_t n0 = rb + tid; n0 < re; n0 += VU * nth) {
+                double sv[VU], dv[VU], xv[VU];
+#pragma unroll
+                for (int u = 0; u < VU; ++u) {
+                    const int64_t n = n0 + u * nth;
+                    if (n < re) { sv[u] = sum[n]; dv[u] = a.d[n]; xv[u] = a.s[n]; }
+                }
+#pragma unroll
+                for (int u = 0; u < VU; ++u) {
+                    const int64_t n = n0 + u * nth;
+                    if (n < re) {
+                        const double tn = dv[u] * sv[u] - xv[u];
+                        a.t[n] = tn;
+                        v3[0] += tn * xv[u];
+                        v3[1] += tn * tn;
+                    }
+                }
+            }
+            if (clk) env.status->t_epi_ns += gtimer() - te;
+        } else if (!op.apply(grid, env, epoch, sc, env.xin[env.rank][0], env.xin[env.rank][1], [&](int64_t n, double sum) {
                 const double sn = a.s[n];
                 const double tn = a.d[n] * sum - sn;
                 a.t[n] = tn;
@@ -695,7 +758,7 @@ __device__ __forceinline__ bool gmres_device(cg::grid_group &grid, const Op &op,
 }
 
 template <class Op>
-__global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_newton_loop(const __grid_constant__ Op op, NewtonArgs a, LoopEnv env) {
+__global__ void __launch_bounds__(Op::kThreads, Op::kMinBlocks) k_newton_loop(const __grid_constant__ Op op, const __grid_constant__ NewtonArgs a, const __grid_constant__ LoopEnv env) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ double smem[SDFS_WARPS * NVAL + NVAL];
@@ -828,7 +891,7 @@ __device__ __forceinline__ void anderson_alphas(const double *G, int m, double r
 }
 
 template <class Op>
-__global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_anderson_loop(const __grid_constant__ Op op, AndersonArgs a, LoopEnv env) {
+__global__ void __launch_bounds__(Op::kThreads, Op::kMinBlocks) k_anderson_loop(const __grid_constant__ Op op, const __grid_constant__ AndersonArgs a, const __grid_constant__ LoopEnv env) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     __shared__ double smem[SDFS_WARPS * NVAL + NVAL];
@@ -925,10 +988,10 @@ __global__ void __launch_bounds__(SDFS_THREADS, Op::kMinBlocks) k_anderson_loop(
 // loops_cont.cu): each instantiates the three loop kernels for ONE operator type, so the
 // three sets compile in parallel.
 // ---------------------------------------------------------------------------
-static int coop_grid(sdfs_ctx *ctx, const void *kern, size_t dyn_smem, int max_per_sm, int64_t work_groups, bool force_full, int *grid_out) {
+static int coop_grid(sdfs_ctx *ctx, const void *kern, int threads, size_t dyn_smem, int max_per_sm, int64_t work_groups, bool force_full, int *grid_out) {
     if (dyn_smem > 0) CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     int per_sm = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SDFS_THREADS, dyn_smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, dyn_smem));
     if (per_sm < 1) return sdfs_set_error(ctx, SDFS_ERR_CUDA, "cooperative kernel does not fit on an SM");
     if (per_sm > max_per_sm) per_sm = max_per_sm;
     int64_t grid = (int64_t)per_sm * ctx->sm_count;
@@ -960,9 +1023,9 @@ static int loop_launch(sdfs_ctx *ctx, Op &lop, void *a, LoopEnv *env, size_t dyn
         if (((const NewtonArgs *)a)->krylov == SDFS_KRYLOV_GMRES) dyn_smem = ((dyn_smem + 15) & ~(size_t)15) + GMRES_WS_BYTES;
     }
     int grid = 0;
-    TRY(coop_grid(ctx, kern, dyn_smem, max_per_sm, work_groups, force_full, &grid));
+    TRY(coop_grid(ctx, kern, Op::kThreads, dyn_smem, max_per_sm, work_groups, force_full, &grid));
     void *args[] = {&lop, a, env};
-    CUDA_TRY(ctx, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(SDFS_THREADS), args, dyn_smem, ctx->stream));
+    CUDA_TRY(ctx, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(Op::kThreads), args, dyn_smem, ctx->stream));
     return SDFS_OK;
 }
 

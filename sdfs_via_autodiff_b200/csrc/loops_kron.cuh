@@ -14,7 +14,7 @@ static int loop_launch_kron_t(sdfs_op *op, void *a, LoopEnv *env) {
     KronLoopOp lop{op->kvs, op->kron_tmp[0], op->kron_tmp[1]};     // this rank's (possibly slab-restricted) view
     const int64_t nloc = op->kvs.row_end - op->kvs.row_begin;
     // every rank must launch (the barriers span all ranks): a rank without rows still gets one CTA
-    return loop_launch<KronLoopOp, WHICH>(ctx, lop, a, env, lop.dyn_smem(), 2, (nloc + SDFS_THREADS - 1) / SDFS_THREADS,
+    return loop_launch<KronLoopOp, WHICH>(ctx, lop, a, env, lop.dyn_smem(), 2, (nloc + KronLoopOp::kThreads - 1) / KronLoopOp::kThreads,
                                            op->kron_sharded /* every rank the same grid: the reduction slots are indexed by CTA */);
 }
 int loop_launch_kron_sa(sdfs_op *op, void *a, LoopEnv *env);

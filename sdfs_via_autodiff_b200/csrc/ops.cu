@@ -85,7 +85,7 @@ k_dense_apply(const __grid_constant__ DenseView dv, const double *x0, const doub
 
 __global__ void __launch_bounds__(256) k_kron_mode(KronView kv, int m, const double *__restrict__ in, double *__restrict__ out) {
     extern __shared__ __align__(16) double kron_smem[];      // factor matrix + per-warp fragment stage
-    kron_mode_apply<true>(kv, m, in, kron_smem, KronSinkStore{out}, KronShare(kron_smem + KRON_SMAT_DOUBLES));
+    kron_mode_apply_regpf(kv, m, in, kron_smem, KronSinkStore{out}, KronShare(kron_smem + KRON_SMAT_DOUBLES));
 }
 
 // 2-D TMA descriptor of the local row slice of P: dims (N columns, nloc rows), row pitch ld,
@@ -385,11 +385,40 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[0], (size_t)N * sizeof(double)));
             CUDA_TRY(ctx, cudaMalloc(&op->kron_tmp[1], (size_t)N * sizeof(double)));
         }
+        const bool sharded = op->kron_sharded;
+        // Large whole operators: elementwise prologue / epilogue kernels at full occupancy around one launch per
+        // mode.  The fused single launch wins while an application is launch- and barrier-bound (0.030 against
+        // 0.039 ms at 10^5 states, 0.058 against 0.068 at 10^6); at 10^7 states the log/exp work dominates and
+        // runs faster at 40+ warps per SM than inside the 16-warp contraction kernel.  SDFS_KRON_SPLIT_MIN
+        // sets the switch-over (states; 0 = never split).
+        static const long long split_min = getenv("SDFS_KRON_SPLIT_MIN") ? atoll(getenv("SDFS_KRON_SPLIT_MIN")) : (1LL << 21);
+        if (!sharded && split_min > 0 && N >= split_min) {
+            k_prologue<true><<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(pmode, N, a_col, d_w, d_v, theta, x0, x1);
+            ctx->launches++;
+            double *sfin[2] = {op->work + 2 * op->ldv, op->work + 3 * op->ldv};
+            const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
+            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
+            for (int pass = 0; pass < nx; ++pass) {
+                const double *in = (pass == 0) ? x0 : x1;
+                for (int m = 0; m < kv.n_modes; ++m) {
+                    double *out = (m == kv.n_modes - 1) ? sfin[pass] : op->kron_tmp[m & 1];
+                    TRY(launch_kron_mode(ctx, kv, m, in, out));
+                    in = out;
+                }
+            }
+            if (prof) {
+                CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
+                ctx->prof_used += 2;
+            }
+            k_epilogue_ew<<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(N, sfin[0], nx > 1 ? sfin[1] : nullptr, e);
+            ctx->launches++;
+            CUDA_TRY(ctx, cudaGetLastError());
+            return SDFS_OK;
+        }
         KronApplyArgs ka{};
         ka.pmode = pmode; ka.w = d_w; ka.v = d_v;
         ka.tmp0 = op->kron_tmp[0]; ka.tmp1 = op->kron_tmp[1];
         ka.s0 = op->work + 2 * op->ldv;
-        const bool sharded = op->kron_sharded;
         PeerArgs pa;
         memset(&pa, 0, sizeof(pa));
         static const bool fused_allowed = !(getenv("SDFS_FUSED_EXCHANGE") && atoi(getenv("SDFS_FUSED_EXCHANGE")) == 0);

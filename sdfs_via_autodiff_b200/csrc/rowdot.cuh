@@ -1022,6 +1022,29 @@ __device__ __forceinline__ void kron_mode_apply(const KronView &kv, int m, const
                                                 KronShare share = KronShare()) {
     kron_mode_apply_ld<PREFETCH, SMALL_FMA, RECT_OK>(kv, m, KronLoadPlain{in}, smat, sink, share);
 }
+// Stand-alone mode kernel (k_kron_mode: one launch per mode - the large-operator path and the batched sweep):
+// a launch has the whole register file for two 256-thread CTAs per SM, so the register-prefetching variant
+// (next tile's fragments held in registers under the current tile's DMMAs) fits, and it is ~10 % faster there
+// than the cp.async-staged one (54 against 62 us per mode at 9.8 M states); the staged variant is what the
+// persistent kernels use, where registers are the scarce resource.
+template <class Sink>
+__device__ __forceinline__ void kron_mode_apply_regpf(const KronView &kv, int m, const double *in, double *smat, Sink &&sink,
+                                                      KronShare share) {
+    const KronMode &md = kv.modes[m];
+    const int n = kv.shape[md.dim];
+    if (md.nout != n || md.colscale || n < KRON_TC_MIN || n > KRON_NMAX_LIMIT || ((n + 7) >> 3) == 2) {
+        kron_mode_apply<true, false, true>(kv, m, in, smat, sink, share);
+        return;
+    }
+    switch ((n + 7) >> 3) {
+    case 3: kron_mode_dmma_reg<3, true>(kv, m, in, smat, sink, share); break;
+    case 4: kron_mode_dmma_reg<4, true>(kv, m, in, smat, sink, share); break;
+    case 5: kron_mode_dmma_reg<5, true>(kv, m, in, smat, sink, share); break;
+    case 6: kron_mode_dmma_reg<6, true>(kv, m, in, smat, sink, share); break;
+    case 7: kron_mode_dmma_reg<7, true>(kv, m, in, smat, sink, share); break;
+    default: kron_mode_dmma_reg<8, true>(kv, m, in, smat, sink, share); break;
+    }
+}
 #define KRON_SMAT_DOUBLES (KRON_NMAX_LIMIT * (KRON_NMAX_LIMIT + 4))
 static_assert(KRON_NMAX_LIMIT == 64, "the restricted-output contraction stages 8 IT x (4 x 16 + 4) doubles");
 

@@ -1,0 +1,43 @@
+"""profiles/r02_scaling.md from the bench lines kept under profiles/ (r02_bench_*.json).
+usage: python tools/make_scaling_md.py > profiles/r02_scaling.md"""
+import glob, json, os, re
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+rows = {}
+for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench_*.json"))):
+    try:
+        d = json.load(open(f))
+    except Exception:
+        continue
+    if d.get("impl") == "reference":
+        continue
+    key = (d["config"].get("storage", "dense"), tuple(d["config"]["shapes"]))
+    rows.setdefault(key, {})[d["n_gpus"]] = (os.path.basename(f), d)
+print("# r02 - multi-GPU runs (one process per GPU, `torchrun bench.py --gpus N --steps 20 --warmup 5 ...`)\n")
+print("Every line carries the `parity` block: T of a seeded w against `oracle.KronSSY.T` on rank 0 (1e-12), identical bytes on")
+print("every rank, Newton outer count against the oracle's own solve.  Times are CUDA events, max over ranks.\n")
+for (storage, shapes), per_n in rows.items():
+    N = 1
+    for s in shapes:
+        N *= s
+    print(f"## {'dense P, row-sharded' if storage == 'dense' else 'factor form, leading-axis slabs'}: SSY {shapes}, N = {N:,}\n")
+    print("| GPUs | evals/s (`value`) | ms per application | speed-up | e2e evals/s | roofline.frac | Newton tol 1e-8 (s) | speed-up | applications | max rel T vs oracle | ranks identical | file |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|---|")
+    base = per_n.get(1, (None, None))[1]
+    for n in sorted(per_n):
+        fn, d = per_n[n]
+        s = d["time_to_fixed_point"] or {}
+        sp = f"{d['value'] / base['value']:.2f}x" if base else "-"
+        sps = f"{base['time_to_fixed_point']['seconds'] / s['seconds']:.2f}x" if base and s else "-"
+        print(f"| {n} | {d['value']:.1f} | {d['ms_per_step']:.4f} | {sp} | {d['e2e']['value']:.1f} | {d['roofline']['frac']:.3f} | "
+              f"{s.get('seconds', float('nan')):.3f} | {sps} | {s.get('operator_applications', '-')} | {d['parity']['max_rel_T']:.1e} | "
+              f"{d['parity']['ranks_identical']} | `{fn}` |")
+    print()
+print("""Notes.
+* Dense: the exchange is fused into the epilogue of `k_dense_apply` (peer stores + flag trade); `e2e` copies w to every rank and
+  reads back only the slab each rank computed.
+* Factor form: each rank receives the (G-1)/G of the vector it does not own every application - 69 MB per rank at 8 ranks and
+  9.8 M states.  With ~0.05 ms of sharded compute the application is exchange-bound: SM-issued peer stores deliver ~230-290 GB/s
+  per rank of NVLink's 900 GB/s.  Operators below 2^22 states are therefore kept whole on every rank (`SDFS_KRON_SHARD_MIN`):
+  at (32,)^4 the sharded application measured 0.100 ms on 8 GPUs against 0.058 ms on one.
+* `tools/mgpu_check.py` (72 checks: T, chained T, P 1 = 1, JVP, SA / Newton / GMRES / Anderson loops, SDF, sweeps, ragged and
+  empty slabs, bit-identity of sharded and whole factor-form operators) passes at 2 and at 8 ranks (`gpurun_out/r02_mgpu*.log`).""")
