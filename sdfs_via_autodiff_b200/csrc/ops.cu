@@ -578,20 +578,25 @@ int sdfs_op_continuous(sdfs_ctx *ctx, int model, const double *h_params, const i
     cv.model = model; cv.D = D; cv.Q = (int)Q; cv.N = N;
     double *dptr = op->cont_mem;
     const double *hg = h_grids;
+    cudaError_t up = cudaSuccess;              // first failing upload (checked once, below: the op must be destroyed)
+    auto upload = [&](double *dst, const double *src, size_t count) {
+        const cudaError_t r = cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        if (up == cudaSuccess) up = r;
+    };
     for (int d = 0; d < D; ++d) {
         cv.n[d] = h_sizes[d];
         cv.grid[d] = dptr;
         cv.g0[d] = hg[0];
         cv.intv[d] = hg[1] - hg[0];
-        cudaMemcpyAsync(dptr, hg, h_sizes[d] * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        upload(dptr, hg, (size_t)h_sizes[d]);
         dptr += h_sizes[d];
         hg += h_sizes[d];
     }
     cv.nodes = dptr;
-    cudaMemcpyAsync(dptr, h_nodes, (size_t)D * Q * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    upload(dptr, h_nodes, (size_t)D * Q);
     dptr += (size_t)D * Q;
     cv.weights = dptr;
-    cudaMemcpyAsync(dptr, h_weights, (size_t)Q * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    upload(dptr, h_weights, (size_t)Q);
     const int np = (model == SDFS_MODEL_SSY) ? 13 : 18;
     for (int i = 0; i < np; ++i) cv.p[i] = h_params[i];
     double psi;
@@ -601,7 +606,8 @@ int sdfs_op_continuous(sdfs_ctx *ctx, int model, const double *h_params, const i
     cv.row_begin = 0;
     cv.row_end = N;      // states are not sharded: every rank evaluates the whole grid
     e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { sdfs_op_destroy(op); return sdfs_set_error(ctx, SDFS_ERR_CUDA, "continuous operator upload: %s", cudaGetErrorString(e)); }
+    if (up != cudaSuccess) e = up;
+    if (e != cudaSuccess) { (void)cudaGetLastError(); sdfs_op_destroy(op); return sdfs_set_error(ctx, SDFS_ERR_CUDA, "continuous operator upload: %s", cudaGetErrorString(e)); }
     *out = op;
     return SDFS_OK;
 }
