@@ -211,7 +211,58 @@ __device__ __forceinline__ double ld_stream1(const double *p) {
 // x^e for x > 0 through exp(e log x): about half the latency of pow() (tools/lat_probe.cu: 443 vs
 // 844 cycles).  Relative error <= ~|e log x| ulp (<= 1e-13 for the calibrations used), which the
 // 1/theta power of T shrinks again by |theta|; NaN for x < 0 and inf for x = 0, e < 0 like pow.
-__device__ __forceinline__ double pow_pos(double x, double e) { return exp(e * log(x)); }
+__device__ __forceinline__ double pow_pos_lib(double x, double e) { return exp(e * log(x)); }
+
+// Table-driven form of the same x^e = exp(e log x) (SDFS_FAST_POW, default on): ~26 fp64 instructions and three
+// L1-resident table gathers instead of ~50 fp64 instructions.  The operator's prologue and epilogue are
+// fp64-PIPE bound (DMMA shares that pipe, profiles/r02_pipe_probe.md), so this is where a factor-form
+// application can still get cheaper.
+//   log x:  x = 2^k m, m in [1,2); i = top 7 mantissa bits; r = m rc[i] - 1 (one FMA, |r| <= 2^-8);
+//           log x = k ln2 + lc[i] + log1p(r), degree-7 polynomial        (rc[i] ~ 1/c_i, lc[i] = -log rc[i] exactly paired)
+//   exp y:  n = rint(64 y / ln2), r = y - n ln2/64 (two FMAs), exp y = 2^(n>>6) e2[n & 63] (1 + r + ... + r^6/720)
+// Validated on the host against long double (tools/gen_fastpow_tables.c + profiles/r02_fastpow.md): exp max relative
+// error 1.9e-16, log max absolute error ~1 ulp of the result, x^e over w in [1, 2000], e in [-50, -5]: 7.3e-14
+// against 5.0e-14 for libm's exp(e log x) - the |e| ulp(log x) term dominates both.  Zero, negative, subnormal,
+// infinite and NaN arguments and results outside the normal range take the library path (NaN for x < 0, inf for
+// x = 0 and e < 0, as the solver loops' NaN semantics require).
+#ifndef SDFS_FAST_POW
+#define SDFS_FAST_POW 1
+#endif
+#if SDFS_FAST_POW
+#include "fastpow_tables.cuh"
+__device__ __forceinline__ double pow_pos(double x, double e) {
+    const unsigned hx = (unsigned)__double2hiint(x);
+    if (hx - 0x00100000u >= 0x7fe00000u) return pow_pos_lib(x, e);          // not a positive normal number
+    const int i = (hx >> 13) & 127;
+    const double m = __hiloint2double((int)((hx & 0x000fffffu) | 0x3ff00000u), __double2loint(x));
+    const double r = fma(m, __ldg(g_fp_rc + i), -1.0);
+    double p = fma(r, 1.0 / 7, -1.0 / 6);
+    p = fma(r, p, 1.0 / 5);
+    p = fma(r, p, -1.0 / 4);
+    p = fma(r, p, 1.0 / 3);
+    p = fma(r, p, -0.5);
+    const double kf = (double)((int)(hx >> 20) - 1023);
+    const double hi = fma(kf, 0x1.62e42fefa38p-1, __ldg(g_fp_lc + i));       // ln2 high part: 32 trailing zero bits, the product is exact
+    const double lg = hi + (r + fma(r * r, p, kf * 0x1.ef35793c7673p-45));
+    const double y = e * lg;
+    if (!(fabs(y) < 700.0)) return exp(y);                                    // over/underflow range, NaN
+    const double t = fma(y, 0x1.71547652b82fep+6, 6755399441055744.0);        // 64 / ln2; magic rounding constant 1.5 * 2^52
+    const int n = __double2loint(t);
+    const double nf = t - 6755399441055744.0;
+    double q = fma(nf, -0x1.62e42fefa38p-7, y);
+    q = fma(nf, -0x1.ef35793c7673p-51, q);
+    double s = fma(q, 1.0 / 720, 1.0 / 120);
+    s = fma(q, s, 1.0 / 24);
+    s = fma(q, s, 1.0 / 6);
+    s = fma(q, s, 0.5);
+    const double em1 = fma(q * q, s, q);
+    const double tj = __ldg(g_fp_e2 + (n & 63));
+    const double v = fma(tj, em1, tj);
+    return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+}
+#else
+__device__ __forceinline__ double pow_pos(double x, double e) { return pow_pos_lib(x, e); }
+#endif
 
 // fp64 tensor-core tile: D(8x8) += A(8x4, row) B(4x8, col).  Lane l holds A[l/4][l%4], B[l%4][l/4]
 // and D[l/4][2(l%4) + {0,1}].  (tcgen05 has no f64 kind; DMMA is the fp64 tensor path on sm_100a.)

@@ -276,8 +276,7 @@ struct KronLoopOp {
         for (int m = 0; m < kv.n_modes; ++m) {
             double *out = (m & 1) ? tmp1 : tmp0;
             kron_mode_store(kv, m, in, out, sc.smat, sc.stage);
-            __threadfence();
-            grid.sync();
+            grid.sync();                        // (orders the stores: cooperative-groups grid barriers fence)
             if (clk) { t1 = gtimer(); if (m < 4) env.status->t_mode_ns[m] += t1 - t0; t0 = t1; }
             in = out;
         }

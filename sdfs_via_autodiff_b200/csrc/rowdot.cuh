@@ -528,12 +528,7 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
     // and a chain of those per tile (shape, stride per axis) showed up as 20 % of the stall samples of the modes
     __shared__ unsigned s_fshape[SDFS_MAX_DIMS];
     __shared__ long long s_fstride[SDFS_MAX_DIMS];
-    __syncthreads();
-    if (threadIdx.x < SDFS_MAX_DIMS) {
-        s_fshape[threadIdx.x] = threadIdx.x < md.nF ? (unsigned)md.Fshape[threadIdx.x] : 1u;
-        s_fstride[threadIdx.x] = threadIdx.x < md.nF ? md.Fstride[threadIdx.x] : 0;
-    }
-    __syncthreads();
+    bool tables_written = false;      // written inside the first matrix staging (between its two barriers)
     const int nF = md.nF;
     const long long Fcount = md.Fcount;
     const long long tpm = (md.Fcount + 7) >> 3;              // fibre tiles per matrix combination
@@ -556,7 +551,14 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
             mbase += c * md.Mstride[a];
         }
         if (mat != cur_mat) {                   // uniform over the CTA
-            __syncthreads();                    // previous matrix no longer in use
+            __syncthreads();                    // previous matrix (and a previous call's decode tables) no longer in use
+            if (!tables_written) {
+                if (threadIdx.x < SDFS_MAX_DIMS) {
+                    s_fshape[threadIdx.x] = threadIdx.x < nF ? (unsigned)md.Fshape[threadIdx.x] : 1u;
+                    s_fstride[threadIdx.x] = threadIdx.x < nF ? md.Fstride[threadIdx.x] : 0;
+                }
+                tables_written = true;
+            }
             const double *msrc = mat0 + (long long)mat * n * n + (long long)out0 * n;
             for (int e0 = threadIdx.x; e0 < IT * 8 * PITCH; e0 += 4 * blockDim.x) {      // four loads in flight per thread
                 double v[4];
