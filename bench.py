@@ -534,7 +534,9 @@ def run_ours(args, shapes):
     else:
         alg_bytes = 80.0 * N * nloc / N                          # 80 N per application, this rank's share
         kern_avg_ms = kern_ms / max(1, kern_n) if kern_n else ms / args.steps
-        kname = "k_kron_apply (one cooperative launch: fused prologue, mode contractions, fused epilogue)"
+        kname = ("k_prologue + k_kron_mode x modes + k_epilogue_ew (factor-form application above 2^21 states, timed as one unit)"
+                 if world == 1 and N >= (1 << 21) else
+                 "k_kron_apply (one cooperative launch: fused prologue, mode contractions, fused epilogue and result exchange)")
     achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")

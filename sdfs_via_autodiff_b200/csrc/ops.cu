@@ -393,11 +393,11 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
         // sets the switch-over (states; 0 = never split).
         static const long long split_min = getenv("SDFS_KRON_SPLIT_MIN") ? atoll(getenv("SDFS_KRON_SPLIT_MIN")) : (1LL << 21);
         if (!sharded && split_min > 0 && N >= split_min) {
+            const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
+            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));     // whole application: prologue .. epilogue
             k_prologue<true><<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(pmode, N, a_col, d_w, d_v, theta, x0, x1);
             ctx->launches++;
             double *sfin[2] = {op->work + 2 * op->ldv, op->work + 3 * op->ldv};
-            const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
-            if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
             for (int pass = 0; pass < nx; ++pass) {
                 const double *in = (pass == 0) ? x0 : x1;
                 for (int m = 0; m < kv.n_modes; ++m) {
@@ -406,12 +406,12 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
                     in = out;
                 }
             }
+            k_epilogue_ew<<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(N, sfin[0], nx > 1 ? sfin[1] : nullptr, e);
+            ctx->launches++;
             if (prof) {
                 CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
                 ctx->prof_used += 2;
             }
-            k_epilogue_ew<<<ew_grid(ctx, N), 256, 0, ctx->stream>>>(N, sfin[0], nx > 1 ? sfin[1] : nullptr, e);
-            ctx->launches++;
             CUDA_TRY(ctx, cudaGetLastError());
             return SDFS_OK;
         }
