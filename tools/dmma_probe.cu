@@ -46,6 +46,29 @@ __global__ void __launch_bounds__(256, 2) k(int iters, double seed, double *out)
 #pragma unroll
             for (int t = 0; t < 4; ++t) acc += c[t][0][0] + c[t][0][1] + c[t][1][0] + c[t][1][1];
         }
+    } else if (MODE == 4) {
+        // two fibre tiles per warp iteration: 14 independent accumulator chains, each B fragment feeds two DMMAs
+#pragma unroll 1
+        for (int i = 0; i < iters; i += 2) {
+            double c[2][IT][2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int it = 0; it < IT; ++it) c[t][it][0] = c[t][it][1] = 0.0;
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) {
+                const double a0 = sa[warp & 3][kt][lane], a1 = sa[(warp + 1) & 3][kt][lane];
+#pragma unroll
+                for (int it = 0; it < IT; ++it) {
+                    const double b = brow[it * 8 * PITCH + kt * 4];
+                    dmma884(c[0][it][0], c[0][it][1], a0, b);
+                    dmma884(c[1][it][0], c[1][it][1], a1, b);
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < IT; ++it) acc += c[0][it][0] + c[0][it][1] + c[1][it][0] + c[1][it][1];
+            if (acc == 1.2345) sa[warp & 3][0][lane] = acc;
+        }
     } else {
         double areg[KT];
 #pragma unroll
@@ -71,17 +94,17 @@ __global__ void __launch_bounds__(256, 2) k(int iters, double seed, double *out)
     }
     if (acc == 12345.678) out[0] = acc;
 }
-template <int MODE> static void run(const char *name, int grid, double *d_out) {
+template <int MODE> static void run(const char *name, int grid, double *d_out, int threads = 256) {
     const int iters = 4000;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k<MODE><<<grid, 256>>>(iters / 8, 0.5, d_out);
+    k<MODE><<<grid, threads>>>(iters / 8, 0.5, d_out);
     cudaDeviceSynchronize();
     float best = 1e30f;
     for (int r = 0; r < 3; ++r) {
-        cudaEventRecord(e0); k<MODE><<<grid, 256>>>(iters, 0.5, d_out); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventRecord(e0); k<MODE><<<grid, threads>>>(iters, 0.5, d_out); cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
-    const double dm = (double)grid * 8 * iters * (MODE == 2 ? 4 * 2 * KT : IT * KT);
+    const double dm = (double)grid * (threads / 32) * iters * (MODE == 2 ? 4 * 2 * KT : IT * KT);
     printf(" \"%s\": {\"ms\": %.3f, \"tflops\": %.2f},\n", name, best, dm * 512.0 / best * 1e-9);
 }
 int main() {
@@ -93,6 +116,12 @@ int main() {
     run<1>("B_from_LDS_per_DMMA", grid, d_out);
     run<3>("B_from_LDS_per_DMMA_A_from_LDS_per_7", grid, d_out);
     run<2>("B_in_registers_4_fibre_tiles_A_from_LDS", grid, d_out);
+    run<4>("two_fibre_tiles_per_iteration_14_chains_16_warps_per_sm", grid, d_out);
+    // how many warps does it take to fill the pipe?  (one CTA per SM, 4 / 8 warps = 1 / 2 per scheduler)
+    run<3>("shipped_loop_1_warp_per_scheduler", grid / 2, d_out, 128);
+    run<4>("two_tiles_1_warp_per_scheduler", grid / 2, d_out, 128);
+    run<3>("shipped_loop_2_warps_per_scheduler", grid / 2, d_out, 256);
+    run<4>("two_tiles_2_warps_per_scheduler", grid / 2, d_out, 256);
     printf(" \"err\": \"%s\"}\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
