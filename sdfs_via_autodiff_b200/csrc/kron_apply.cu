@@ -1,5 +1,11 @@
 // The fused factor-form apply kernel in its own translation unit (its tensor-core contraction variants are
 // the slowest code of the library to compile; the build runs one nvcc per unit in parallel).
+#ifndef KRON_APPLY_CTAS
+#define KRON_APPLY_CTAS 2         // CTAs per SM of the fused apply (3 = 256 threads at <= 85 registers with a single-buffered stage: measured no gain)
+#endif
+#if KRON_APPLY_CTAS >= 3
+#define KRON_STAGE_BUFS 1
+#endif
 #include "common.cuh"
 #include "rowdot.cuh"
 #include "epilogue.cuh"
@@ -48,7 +54,7 @@ struct KronEpi {
     }
 };
 
-__global__ void __launch_bounds__(KRON_APPLY_THREADS, 2)
+__global__ void __launch_bounds__(KRON_APPLY_THREADS, KRON_APPLY_CTAS)
 k_kron_apply(const __grid_constant__ KronView kv, const __grid_constant__ KronApplyArgs a, const __grid_constant__ KronEpi epi) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double kron_smem[];
@@ -62,7 +68,7 @@ int launch_kron_apply(sdfs_ctx *ctx, const KronView &kv, const KronApplyArgs &ka
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_kron_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KRON_APPLY_SMEM));
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kron_apply, KRON_APPLY_THREADS, KRON_APPLY_SMEM));
         if (per_sm < 1) return sdfs_set_error(ctx, SDFS_ERR_CUDA, "k_kron_apply does not fit on an SM");
-        if (per_sm > 2) per_sm = 2;
+        if (per_sm > KRON_APPLY_CTAS) per_sm = KRON_APPLY_CTAS;
     }
     if (kv.n_modes < 2) return sdfs_set_error(ctx, SDFS_ERR_UNSUPPORTED, "factor-form apply needs at least two modes");
     // persistent grid: every CTA takes one contiguous range of fibre tiles per mode; small grids get fewer

@@ -508,7 +508,10 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, 
     const int sz = valid ? 8 : 0;                            // 0: nothing is read, the 8 bytes are zero-filled
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gsrc), "r"(sz) : "memory");
 }
-#define KRON_STAGE_DOUBLES_PER_WARP (2 * 16 * 32)
+#ifndef KRON_STAGE_BUFS
+#define KRON_STAGE_BUFS 2          // fragment stage buffers per warp: 2 = the next tile is fetched while the current one is
+#endif                             // contracted; 1 = fetched once the current fragments are consumed (half the shared memory: a third CTA per SM)
+#define KRON_STAGE_DOUBLES_PER_WARP (KRON_STAGE_BUFS * 16 * 32)
 template <int IT /* 8-row output tiles */, bool EXACT /* n > 8 (IT - 1): straight-line k loop */, bool RECT, class Load, class Sink>
 __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &&load, double *smat, Sink &&sink,
                                                KronShare share = KronShare()) {
@@ -616,7 +619,7 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
         const double *brow = smat + g * PITCH + q;
         while (t < seg_end) {
             const long long tn = t + nwarps;
-            if (tn < seg_end) {
+            if (KRON_STAGE_BUFS == 2 && tn < seg_end) {
                 fetch_tile(tn, buf ^ 1, bn, vn);
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
             } else {
@@ -656,6 +659,7 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
                     for (int it = 0; it < IT; ++it) dmma884(c[it][0], c[it][1], a, brow[it * 8 * PITCH + kt * 4]);
                 }
             }
+            if (KRON_STAGE_BUFS == 1 && !STAGED && tn < seg_end) fetch_tile(tn, 0, bn, vn);     // fragments consumed: refill under the stores
             if constexpr (STAGED) {               // sink arithmetic from the stage, rolled (four outputs per trip)
                 // the sink's per-row factor (a_row) for all 2 IT outputs first: every load in flight at once
                 // instead of one exposed latency per trip; c is dead after this block
@@ -730,8 +734,9 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
                     idx += 8 * kstride;
                 }
             }
+            if (KRON_STAGE_BUFS == 1 && STAGED && tn < seg_end) fetch_tile(tn, 0, bn, vn);      // the staged sink used the buffer
             base = bn; fv = vn;
-            buf ^= 1;
+            if (KRON_STAGE_BUFS == 2) buf ^= 1;
             t = tn;
         }
         seg = seg_end;
