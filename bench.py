@@ -544,7 +544,8 @@ def run_ours(args, shapes):
         try:
             tj = json.load(open(tp))
             for ent in (tj if isinstance(tj, list) else [tj]):
-                if ent.get("shapes") == list(shapes) and ent.get("n_gpus") == world and ent.get("storage", "dense") == args.storage:
+                want = args.storage if not (kron and world == 1 and N >= (1 << 21)) else "kron_split"    # which kernels ran
+                if ent.get("shapes") == list(shapes) and ent.get("n_gpus") == world and ent.get("storage", "dense") == want:
                     traffic = ent.get("bytes_per_launch", ent.get("k_dense_apply_bytes_per_launch"))
         except Exception:
             traffic = None
