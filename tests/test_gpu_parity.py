@@ -940,6 +940,36 @@ def test_factor_form_axes_longer_than_64_use_the_cached_load_pass():
     np.testing.assert_allclose(np.asarray(ws), ref, rtol=1e-11)
 
 
+def test_factor_form_shortest_axes():
+    """The shortest axes the discretisers allow (2 states; quantecon's rouwenhorst rejects 1) in every position,
+    factor form: T, JVP, P 1 = 1 and the SDF pass against the oracle / the dense storage (the fused apply's loader,
+    sink and two-contraction paths on the FMA kernel, next to one tensor-core axis)."""
+    for model, shapes in (("ssy", (2, 2, 2, 2)), ("ssy", (2, 3, 2, 2)), ("ssy", (2, 2, 2, 9)), ("ssy", (12, 2, 2, 2)),
+                          ("gcy", (2, 2, 2, 3, 2, 2)), ("gcy", (3, 2, 2, 2, 2, 10))):
+        if model == "ssy":
+            mdl = O.SSY(); arrays = O.discretize_ssy(mdl, shapes); kop = O.KronSSY(shapes, mdl.params, arrays)
+            op = S.make_T_ssy(mdl, shapes, arrays, storage="kron"); dn = S.make_T_ssy(mdl, shapes, arrays, storage="dense")
+        else:
+            mdl = O.GCY(); arrays = O.discretize_gcy(mdl, shapes); kop = O.KronGCY(shapes, mdl.params, arrays)
+            op = S.make_T_gcy(mdl, shapes, arrays, storage="kron"); dn = S.make_T_gcy(mdl, shapes, arrays, storage="dense")
+        rng = np.random.default_rng(11)
+        w = 400 + 500 * rng.random(shapes)
+        v = rng.standard_normal(shapes)
+        np.testing.assert_allclose(np.asarray(op(w)), kop.T(w), rtol=RTOL_T, err_msg=str(shapes))
+        np.testing.assert_allclose(np.asarray(op.jvp(w, v)), kop.jvp(w, v), rtol=1e-10, atol=1e-11, err_msg=str(shapes))
+        np.testing.assert_allclose(np.asarray(op.apply_P(np.ones(shapes))), 1.0, rtol=0, atol=1e-12, err_msg=str(shapes))
+        qk, ek = op.sdf(w)
+        qd, ed = dn.sdf(w)
+        np.testing.assert_allclose(np.asarray(qk), np.asarray(qd), rtol=1e-11, err_msg=str(shapes))
+        np.testing.assert_allclose(np.asarray(ek), np.asarray(ed), rtol=1e-9, atol=1e-11, err_msg=str(shapes))
+        ws, k = S.successive_approx(op, w, tol=0.0, max_iter=3, verbose=False)
+        ref = w.copy()
+        for _ in range(3):
+            ref = kop.T(ref)
+        np.testing.assert_allclose(np.asarray(ws), ref, rtol=1e-11, err_msg=str(shapes))
+        del op, dn
+
+
 def test_factor_form_random_shapes_against_oracle():
     """Seeded random grids (axes 2..26, ragged fibre tiles, partial k and output tiles, every mix of
     the FMA / tensor-core / multi-tile code paths): T and the JVP of the factor form against the
