@@ -356,6 +356,12 @@ int small_sa_try(sdfs_op *op, const double *d_w_init, double tol, int64_t max_it
     const DenseView &dv = op->dv;
     if (dv.row_begin != 0 || dv.row_end != dv.N) return 0;
     const int64_t N = dv.N;
+    // a dense operator that was built from factors still has them: between 161 and 8192 states successive
+    // approximation is fastest as the one-CTA factor-form kernel (5.5 us per iteration at 729 states against
+    // 7 us per iteration for the dense cooperative loop), while Newton on the same operator uses the dense pass
+    // (18 us per application against 54 us for six factor-form modes) - storage "auto" relies on this
+    if (N > SMALL_MAX_N && op->factors != nullptr && op->kv.n_modes >= 2)
+        return small_sa_kron_try(op, d_w_init, tol, max_iter, d_w_out, d_err_hist, hist_stride, hist_cap);
     if (N > SMALL_MAX_N) return 0;
     const size_t smem = ((size_t)N * N + 2 * N + 64) * sizeof(double);
     if (smem > 220 * 1024) return 0;

@@ -109,11 +109,16 @@ class WCOperator:
         ctx = factors.ctx
         N = int(np.prod(factors.shapes))
         if storage == "auto":
-            # up to 160 states the dense P lives in the registers / shared memory of one CTA (1.3 us per SA
-            # iteration); above that the factor form is faster everywhere (3x at 10^4 states, and dense P is
-            # impossible beyond ~1.5 10^5), so "auto" never materialises a large P - ask for "dense" to get one
-            storage = "dense" if N <= 160 else "kron"
-        st = {"dense": STORAGE_DENSE, "kron": STORAGE_KRON, "kron_local": STORAGE_KRON_LOCAL}[storage]
+            # up to 4096 states (P <= 134 MB) a dense P serves both solvers best: Newton's mat-vecs are one 18 us pass
+            # over an L2-resident matrix (six factor-form modes cost 54 us on the reference's default GCY grid), and
+            # successive approximation runs as a one-CTA kernel either way (P in registers up to 160 states, the
+            # factor form in shared memory above: the operator keeps its factors).  Beyond that the factor form is
+            # faster everywhere (3x at 10^4 states; dense P is impossible beyond ~1.5 10^5), so "auto" never
+            # materialises a large P - ask for "dense" to get one.  In a multi-rank context the small dense P is
+            # replicated, not row-sharded (cross-rank barriers would cost more than the work).
+            storage = ("dense_replicated" if ctx.nranks > 1 else "dense") if N <= 4096 else "kron"
+        st = {"dense": STORAGE_DENSE, "kron": STORAGE_KRON, "kron_local": STORAGE_KRON_LOCAL,
+              "dense_replicated": 2}[storage]
         h = C.c_void_p()
         check(lib.sdfs_op_from_factors(ctx.handle, factors.handle, st, C.byref(h)), ctx.handle)
         return cls(ctx, h, factors.shapes, keep=[factors])
