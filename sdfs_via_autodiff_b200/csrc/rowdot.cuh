@@ -531,6 +531,12 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
     // and a chain of those per tile (shape, stride per axis) showed up as 20 % of the stall samples of the modes
     __shared__ unsigned s_fshape[SDFS_MAX_DIMS];
     __shared__ long long s_fstride[SDFS_MAX_DIMS];
+    // division by the (run-time, per-mode constant) free-axis lengths as multiply-high + shift: for d >= 1 and
+    // s = 31 + ceil(log2 d), M = floor(2^s / d) + 1 fits 32 bits and (r M) >> s = floor(r / d) for every r < 2^31
+    // (M d - 2^s lies in (0, d], so r (M d - 2^s) < 2^31 d <= 2^s).  ~5 instructions per axis instead of the
+    // ~25 of a 32-bit hardware-assisted division; the decode runs once per fibre tile and lane.
+    __shared__ unsigned s_fmagic[SDFS_MAX_DIMS];
+    __shared__ int s_fsh[SDFS_MAX_DIMS];
     bool tables_written = false;      // written inside the first matrix staging (between its two barriers)
     const int nF = md.nF;
     const long long Fcount = md.Fcount;
@@ -541,6 +547,7 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
     const long long t_begin = T * share.cta / share.nctas, t_end = T * (share.cta + 1) / share.nctas;
     const long long kstride = md.stride;
     const bool small_f = Fcount < (1LL << 31);            // 32-bit index decode (always, in practice)
+    const int ktv_lane = (n - q + 3) >> 2;                // number of k steps with 4 kt + q < n for this lane
     int cur_mat = -1;
     for (long long seg = t_begin; seg < t_end;) {
         const long long mc = seg / tpm;
@@ -557,8 +564,12 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
             __syncthreads();                    // previous matrix (and a previous call's decode tables) no longer in use
             if (!tables_written) {
                 if (threadIdx.x < SDFS_MAX_DIMS) {
-                    s_fshape[threadIdx.x] = threadIdx.x < nF ? (unsigned)md.Fshape[threadIdx.x] : 1u;
+                    const unsigned d = threadIdx.x < nF ? (unsigned)md.Fshape[threadIdx.x] : 1u;
+                    const int sh = 31 + (d > 1 ? 32 - __clz((int)(d - 1)) : 0);
+                    s_fshape[threadIdx.x] = d;
                     s_fstride[threadIdx.x] = threadIdx.x < nF ? md.Fstride[threadIdx.x] : 0;
+                    s_fmagic[threadIdx.x] = (unsigned)((1ULL << sh) / d + 1ULL);
+                    s_fsh[threadIdx.x] = sh;
                 }
                 tables_written = true;
             }
@@ -589,8 +600,8 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
             if (small_f) {
                 unsigned r2 = fv ? (unsigned)f : 0u;
                 for (int ax = nF - 1; ax >= 0; --ax) {
-                    const unsigned sh = s_fshape[ax], qd = r2 / sh;
-                    base += (long long)(r2 - qd * sh) * s_fstride[ax];
+                    const unsigned qd = (unsigned)(((unsigned long long)r2 * s_fmagic[ax]) >> s_fsh[ax]);
+                    base += (long long)(r2 - qd * s_fshape[ax]) * s_fstride[ax];
                     r2 = qd;
                 }
             } else {
@@ -603,10 +614,11 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
             }
             const double *p = load.ptr(base + q * kstride);
             double *dst = stw + buf * (16 * 32);
+            const int ktv = fv ? ktv_lane : 0;       // k steps this lane has data for (4 kt + q < n), none for a padding fibre
 #pragma unroll
             for (int kt = 0; kt < KT; ++kt) {
                 if (EXACT && !RECT ? (kt < KT - 1 || kt < kt_n) : kt < kt_n)
-                    cp_async8(dst + kt * 32, p, fv && kt * 4 + q < n);
+                    cp_async8(dst + kt * 32, p, kt < ktv);
                 p += 4 * kstride;
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
