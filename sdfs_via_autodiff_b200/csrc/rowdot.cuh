@@ -629,6 +629,9 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
         int buf = 0;
         if (t < seg_end) fetch_tile(t, 0, base, fv);
         const double *brow = smat + g * PITCH + q;
+#ifdef KRON_DBG_NO_B_LDS
+        const double dbg_b = brow[0];
+#endif
         while (t < seg_end) {
             const long long tn = t + nwarps;
             if (KRON_STAGE_BUFS == 2 && tn < seg_end) {
@@ -667,8 +670,13 @@ __device__ __forceinline__ void kron_mode_dmma(const KronView &kv, int m, Load &
             for (int kt = 0; kt < KT; ++kt) {
                 if (EXACT && !RECT ? (kt < KT - 1 || kt < kt_n) : kt < kt_n) {
                     const double a = st[kt * 32];
+#ifdef KRON_DBG_NO_B_LDS      /* timing experiment only (wrong results): B operands from registers, no LDS in the DMMA loop */
+#pragma unroll
+                    for (int it = 0; it < IT; ++it) dmma884(c[it][0], c[it][1], a, (it & 1) ? a : dbg_b);
+#else
 #pragma unroll
                     for (int it = 0; it < IT; ++it) dmma884(c[it][0], c[it][1], a, brow[it * 8 * PITCH + kt * 4]);
+#endif
                 }
             }
             if (KRON_STAGE_BUFS == 1 && !STAGED && tn < seg_end) fetch_tile(tn, 0, bn, vn);     // fragments consumed: refill under the stores
