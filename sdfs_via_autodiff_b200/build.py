@@ -27,7 +27,9 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    if any(not os.path.exists(os.path.join(CSRC, src.replace(".cu", ".o"))) for src in SOURCES):
+        return True                          # an object is missing: the library was not produced by this script's last run
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".o")]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "sdfs_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
