@@ -285,6 +285,44 @@ def parity_block(S, ctx, op, kop, shapes, dist, rank, world, solve):
     return out
 
 
+def sharded_factor_form_block(S, ctx, dist, rank, world, barrier, max_over_ranks, shp=(56, 56, 56, 56)):
+    """SSY (56,)^4 = 9.8 M states in factor form on all ranks (leading-axis slabs): application time, Newton solve,
+    parity of T against the oracle on rank 0 and identical bytes on every rank."""
+    import hashlib
+    op = S.make_T_ssy(S.SSY(), shp, storage="kron", ctx=ctx)
+    N = op.N
+    w = ctx.full(shp, 800.0)
+    for _ in range(3):
+        w = op(w)
+    barrier()
+    ms, w = _timed_chain(ctx, op, w, 20)
+    ms = max_over_ranks(ms) / 20
+    S.newton_solver(op, ctx.full(shp, 800.0), verbose=False)
+    barrier()
+    t0 = time.perf_counter()
+    wn, k, info = S.newton_solver(op, ctx.full(shp, 800.0), verbose=False, return_info=True)
+    ctx.sync()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    rng = np.random.default_rng(1233)
+    w_seed = np.exp(rng.standard_normal(shp))
+    got = np.asarray(op(w_seed))
+    all_d = [None] * world
+    dist.all_gather_object(all_d, hashlib.sha1(got.tobytes()).hexdigest())
+    out = {"shapes": list(shp), "N": N, "rows_of_rank0": [op.row_begin, op.row_end], "sharded": op.row_end - op.row_begin < N,
+           "T_ms": ms, "evals_per_s": 1e3 / ms, "newton_seconds": dt, "newton_outer": int(k),
+           "newton_applications": int(info["matvecs"]), "ranks_identical": len(set(all_d)) == 1}
+    if rank == 0:
+        import oracle as O
+        ssy = O.SSY()
+        ko = O.KronSSY(shp, ssy.params, O.discretize_ssy(ssy, shp))
+        out["T_max_rel_vs_oracle"] = float(np.max(np.abs(got / ko.T(w_seed) - 1)))
+        wn_h = np.asarray(wn)
+        out["newton_residual_l2_by_oracle"] = float(np.linalg.norm((ko.T(wn_h) - wn_h).ravel()))
+        out["ok"] = bool(out["T_max_rel_vs_oracle"] < 1e-12 and out["ranks_identical"] and out["newton_residual_l2_by_oracle"] <= 1.01e-4)
+    del op
+    return out
+
+
 def extra_configs(S, ctx, peak):
     """BASELINE configs C1, C3, C4, C5 on one GPU, each with its own parity scalar against the oracle
     (`value` stays on C2).  Wall clock for whole solves, CUDA events for single applications."""
@@ -451,7 +489,7 @@ def run_ours(args, shapes):
         import torch.distributed as dist
         dist.init_process_group("gloo", init_method="env://")
         from sdfs_via_autodiff_b200 import dist as sd
-        sd.init_comm(ctx, rank, world, dist, max_N=int(np.prod(shapes)))
+        sd.init_comm(ctx, rank, world, dist, max_N=max(int(np.prod(shapes)), 56 ** 4 if not args.no_configs else 0))
     S.Context._default = ctx
     N = int(np.prod(shapes))
     kron = args.storage == "kron"
@@ -612,6 +650,10 @@ def run_ours(args, shapes):
             dk = max_over_ranks(time.perf_counter() - t0)
             solve["factor_form"] = {"seconds": dk, "outer_iters": int(kk), "operator_applications": int(ik["matvecs"]),
                                     "max_rel_vs_dense_storage": float(np.max(np.abs(np.asarray(wk2) / solve["_w"] - 1)))}
+    # ---- BASELINE configs[3] in the same line at N > 1: the 9.8 M-state factor-form operator, slab-sharded over the ranks
+    # (at N = 1 the same grid is in extra.configs.C4)
+    if world > 1 and not kron and not args.no_configs:
+        extra["config4_factor_form_sharded"] = sharded_factor_form_block(S, ctx, dist, rank, world, barrier, max_over_ranks)
     parity = parity_block(S, ctx, op, kop, shapes, dist, rank, world, solve)
     if solve is not None:
         solve.pop("_w", None)
@@ -652,6 +694,9 @@ def run_ours(args, shapes):
             rc = 3
         if configs and any(isinstance(v, dict) and v.get("ok") is False for v in configs.values()):
             sys.stderr.write("PARITY FAILURE in extra.configs\n")
+            rc = 3
+        if extra.get("config4_factor_form_sharded", {}).get("ok") is False:
+            sys.stderr.write("PARITY FAILURE in extra.config4_factor_form_sharded\n")
             rc = 3
     if dist:
         dist.barrier()
