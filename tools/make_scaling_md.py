@@ -35,9 +35,12 @@ for (storage, shapes), per_n in rows.items():
 print("""Notes.
 * Dense: the exchange is fused into the epilogue of `k_dense_apply` (peer stores + flag trade); `e2e` copies w to every rank and
   reads back only the slab each rank computed.
-* Factor form: each rank receives the (G-1)/G of the vector it does not own every application - 69 MB per rank at 8 ranks and
-  9.8 M states.  With ~0.05 ms of sharded compute the application is exchange-bound: SM-issued peer stores deliver ~230-290 GB/s
-  per rank of NVLink's 900 GB/s.  Operators below 2^22 states are therefore kept whole on every rank (`SDFS_KRON_SHARD_MIN`):
-  at (32,)^4 the sharded application measured 0.100 ms on 8 GPUs against 0.058 ms on one.
+* Factor form: a single application cannot scale - the API hands every rank the full w and wants the full Tw back, so every rank
+  evaluates the w^theta prologue for ALL N states inside the leading contraction (40 us of fp64-pipe time, 78.7 MB read) and must
+  receive the (G-1)/G of the result it did not compute (69 MB per rank at 8 ranks: >= 77 us at NVLink 5's 900 GB/s, ~0.2 ms
+  measured; the NCCL all-gather path, SDFS_FUSED_EXCHANGE=0, gives the same 0.322 ms at 8 ranks).  Inside the solver loops the
+  prologue, the Krylov vector phases and the dot products ARE sharded: Newton gains 1.45-1.6x.  Operators below 2^22 states are
+  kept whole on every rank (`SDFS_KRON_SHARD_MIN`): at (32,)^4 the sharded application measured 0.100 ms on 8 GPUs against 0.058 ms
+  on one.
 * `tools/mgpu_check.py` (72 checks: T, chained T, P 1 = 1, JVP, SA / Newton / GMRES / Anderson loops, SDF, sweeps, ragged and
-  empty slabs, bit-identity of sharded and whole factor-form operators) passes at 2 and at 8 ranks (`gpurun_out/r02_mgpu*.log`).""")
+  empty slabs, bit-identity of sharded and whole factor-form operators) passes at 2, 4 and 8 ranks (`gpurun_out/r02_mgpu*.log`).""")
