@@ -443,7 +443,6 @@ def extra_configs(S, ctx, peak):
     kms, kn = ctx.prof_read()
     ctx.prof_enable(0)
     kms /= max(1, kn)
-    S.newton_solver(op, ctx.full(shapes, 800.0), max_iter=1, verbose=False) if False else None
     t0 = time.perf_counter()
     wn, k, info = S.newton_solver(op, ctx.full(shapes, 800.0), verbose=False, return_info=True)
     ctx.sync()
