@@ -119,3 +119,32 @@ def test_sweep_front_end_argument_checks():
     with pytest.raises(ValueError):
         _prefs(np.ones((3, 2)))
     assert _prefs([[8.89, 1.97, 0.999]]).shape == (1, 3)
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) on a tiny grid: one JSON line with
+    the contract's keys, every timed step a FULL evaluation of the reference's broadcast-sum (nothing extrapolated),
+    checked against the sum-factorised oracle; ranks other than 0 print nothing."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--shapes", "3,3,4,5", "--steps", "2",
+           "--warmup", "1", "--cpu-threads", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["dtype"] == "f64"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 2 and cb["full_evaluations"] is True and "nothing extrapolated" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # value = full evaluations per second: ms_per_step is the time of ONE evaluation
+    np.testing.assert_allclose(d["value"], 1e3 / d["ms_per_step"], rtol=1e-9)
+    assert d["cpu_factored"]["value"] > 0
+    # non-zero ranks of a torchrun launch stay silent and exit 0
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
