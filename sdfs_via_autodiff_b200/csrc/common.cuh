@@ -164,6 +164,7 @@ struct sdfs_op {
     int sweep_form = 0;                // SDFS_SWEEP_DENSE | SDFS_SWEEP_FACTOR
     bool kron_sharded = false;         // factor form with the leading axis split into per-rank slabs
     double *a_col_lead = nullptr;      // a_col along the axis of the first contraction (it is constant along the others)
+    double *dense_tail = nullptr;      // DenseTail scratch of the dense application (rowdot.cuh): segment partials, then counters
 };
 
 int op_ensure_work(sdfs_op *op, int n_vectors);

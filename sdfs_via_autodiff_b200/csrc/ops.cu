@@ -67,7 +67,7 @@ __global__ void k_epilogue_ew(int64_t N, const double *__restrict__ s0, const do
 template <int NX>
 __global__ void __launch_bounds__(SDFS_THREADS, 1)
 k_dense_apply(const __grid_constant__ DenseView dv, const double *x0, const double *x1, EpiArgs e,
-              const __grid_constant__ PeerArgs pa) {
+              const __grid_constant__ PeerArgs pa, DenseTail tail) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     RowPipe<NX> *rp = reinterpret_cast<RowPipe<NX> *>(dyn_smem);
     PipeState st;
@@ -76,10 +76,10 @@ k_dense_apply(const __grid_constant__ DenseView dv, const double *x0, const doub
         dense_pass<NX>(dv, x0, x1, rp, st, [&](int64_t n, double s0, double s1) {
             const double val = epilogue_value(e, n, s0, s1);
             for (int r = 0; r < pa.nranks; ++r) pa.out[r][n] = val;
-        });
+        }, tail);
         peer_exchange_finish(pa);
     } else {
-        dense_pass<NX>(dv, x0, x1, rp, st, [&](int64_t n, double s0, double s1) { apply_epilogue<false>(e, n, s0, s1); });
+        dense_pass<NX>(dv, x0, x1, rp, st, [&](int64_t n, double s0, double s1) { apply_epilogue<false>(e, n, s0, s1); }, tail);
     }
 }
 
@@ -210,15 +210,33 @@ static inline int dense_grid(sdfs_ctx *ctx, const DenseView &dv) {
     return (int)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
+// last partial wave of row groups split by columns over the whole grid (rowdot.cuh, DenseTail);
+// SDFS_DENSE_TAIL=0 keeps whole groups (the A/B switch of profiles/r02_dense_tail.md)
+static int op_dense_tail(sdfs_op *op, DenseTail *tail) {
+    sdfs_ctx *ctx = op->ctx;
+    static const bool tail_allowed = !(getenv("SDFS_DENSE_TAIL") && atoi(getenv("SDFS_DENSE_TAIL")) == 0);
+    tail->buf = nullptr; tail->cnt = nullptr;
+    if (!tail_allowed || !op->dv.vec2) return SDFS_OK;
+    const size_t part_bytes = (size_t)ctx->sm_count * 2 * TR * sizeof(double);
+    if (!op->dense_tail) {
+        const size_t bytes = part_bytes + (size_t)ctx->sm_count * sizeof(unsigned int);
+        CUDA_TRY(ctx, cudaMalloc(&op->dense_tail, bytes));
+        CUDA_TRY(ctx, cudaMemsetAsync(op->dense_tail, 0, bytes, ctx->stream));
+    }
+    tail->buf = op->dense_tail;
+    tail->cnt = (unsigned int *)((char *)op->dense_tail + part_bytes);
+    return SDFS_OK;
+}
+
 template <int NX>
 static int launch_dense_apply(sdfs_ctx *ctx, const DenseView &dv, const double *x0, const double *x1, const EpiArgs &e,
-                              const PeerArgs &pa) {
+                              const PeerArgs &pa, DenseTail tail) {
     const size_t smem = dv.vec2 ? sizeof(RowPipe<NX>) : 0;
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_dense_apply<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(RowPipe<NX>)));
     const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
     if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
-    k_dense_apply<NX><<<dense_grid(ctx, dv), SDFS_THREADS, smem, ctx->stream>>>(dv, x0, x1, e, pa);
+    k_dense_apply<NX><<<dense_grid(ctx, dv), SDFS_THREADS, smem, ctx->stream>>>(dv, x0, x1, e, pa, tail);
     if (prof) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
         ctx->prof_used += 2;
@@ -369,8 +387,10 @@ static int run_apply(sdfs_op *op, int pmode, const double *d_w, const double *d_
         }
         // a rank without rows still takes part in the exchange (one CTA, empty pass)
         if (op->dv.row_end > op->dv.row_begin || fused) {
-            if (nx == 1) TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e, pa));
-            else TRY(launch_dense_apply<2>(ctx, op->dv, x0, x1, e, pa));
+            DenseTail tail;
+            TRY(op_dense_tail(op, &tail));
+            if (nx == 1) TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e, pa, tail));
+            else TRY(launch_dense_apply<2>(ctx, op->dv, x0, x1, e, pa, tail));
         }
         CUDA_TRY(ctx, cudaGetLastError());
         if (fused) {
@@ -624,6 +644,7 @@ int sdfs_op_destroy(sdfs_op *op) {
     if (op->own_e_sdf) cudaFree(op->own_e_sdf);
     if (op->work) cudaFree(op->work);
     if (op->slots) cudaFree(op->slots);
+    if (op->dense_tail) cudaFree(op->dense_tail);
     if (op->kron_tmp[0]) cudaFree(op->kron_tmp[0]);
     if (op->kron_tmp[1]) cudaFree(op->kron_tmp[1]);
     if (op->a_col_lead) cudaFree(op->a_col_lead);
@@ -727,9 +748,11 @@ int sdfs_op_bench_pass(sdfs_op *op, int mode, int reps, double *avg_ms) {
     e.inv_theta = 1.0 / e.theta;
     PeerArgs pa;
     memset(&pa, 0, sizeof(pa));                 // local pass only
-    TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e, pa));
+    DenseTail tail;
+    TRY(op_dense_tail(op, &tail));
+    TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e, pa, tail));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int i = 0; i < reps; ++i) TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e, pa));
+    for (int i = 0; i < reps; ++i) TRY(launch_dense_apply<1>(ctx, op->dv, x0, x0, e, pa, tail));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
     float ms = 0.f;

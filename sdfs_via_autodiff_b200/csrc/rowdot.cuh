@@ -14,8 +14,9 @@
 //   of every LDG variant.
 // Fallback path (odd leading dimension / unaligned user P): per-warp rows with
 //   8-byte streaming loads.
-// In both paths a row's result depends only on (N, path), never on the grid size
-// or the row sharding, so multi-GPU runs reproduce single-GPU rows bit for bit.
+// A row's result is a fixed-order sum for a given (N, path, position of its group in the CTA's schedule): runs repeat
+// bit for bit; across grid sizes and row shardings the order of the eight per-warp partials (and, for the groups of the
+// last partial wave, the column segments - see DenseTail) differs, i.e. rows agree to rounding (~1e-16 relative).
 #pragma once
 #include "common.cuh"
 
@@ -92,27 +93,58 @@ __device__ __forceinline__ void pipe_init(RowPipe<NX> *rp, PipeState &st) {
 // epi(n_global, s0, s1) runs on thread r (< rows in group) of warp 0.
 // Preconditions: dv.vec2 (dv.tm valid), x0/x1 16-byte aligned, readable and finite up to
 // index round_up(N, 2).  `dv` must live in kernel parameter space (__grid_constant__).
+// Tail split (optional, `tail.buf` non-null): the groups beyond the last FULL wave of the grid -- R = ngroups mod grid
+// of them -- keep R CTAs streaming while the rest of the chip idles.  When R is small (S = grid / R >= 8 segments) each of
+// those groups is cut into S column segments, one per CTA; a segment's row partials go to `tail.buf`, and the CTA that
+// arrives last at the group's counter adds the S segments in segment order and runs the epilogue: same result whichever
+// CTA finishes last.  Measured on one rank's slab of the 88 GB operator (tools/dense_tail.py, profiles/r02_dense_tail.md):
+// 13 122 rows (R = 13, S = 11) 1521 -> 1509 us, against 1505 us for a perfectly divisible slab.  A partial wave with many
+// CTAs (R = 25, 49: 4 and 2 ranks) already streams at the full HBM rate and the split only adds its combine (+16 / +24 us),
+// hence the threshold.
+#define DENSE_TAIL_MIN_SPLIT 8
+struct DenseTail {
+    double *buf;            // [grid][2][TR] segment partials (slot = CTA)
+    unsigned int *cnt;      // [grid] arrivals per tail group, zero between passes (the last arriver resets its counter)
+};
+
 template <int NX, class Epi>
 __device__ __forceinline__ void dense_pass_tma(const DenseView &dv, const double *x0, const double *x1,
-                                               RowPipe<NX> *rp, PipeState &st, Epi &&epi) {
+                                               RowPipe<NX> *rp, PipeState &st, Epi &&epi, DenseTail tail = DenseTail{nullptr, nullptr}) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nloc = dv.row_end - dv.row_begin;
     const int64_t ngroups = (nloc + TR - 1) / TR;
     const int64_t ncols = (dv.N + 1) & ~(int64_t)1;          // x columns to move (even count)
     const uint32_t nck = (uint32_t)((dv.N + TCW - 1) / TCW);
     const uint32_t t_begin = st.t;
+    // whole groups: g = blockIdx.x + k gridDim.x below g_main; then at most one column segment of a tail group
+    int64_t g_main = ngroups;
+    int tail_r = 0, tail_s = 0;                               // tail groups, segments per tail group
+    if (tail.buf) {
+        const int r = (int)(ngroups % gridDim.x);
+        if (r > 0 && ngroups > (int64_t)gridDim.x && (int)gridDim.x / r >= DENSE_TAIL_MIN_SPLIT && nck >= 64) {
+            tail_r = r; tail_s = (int)gridDim.x / r; g_main = ngroups - r;
+        }
+    }
+    const int64_t my_groups = (g_main > (int64_t)blockIdx.x) ? (g_main - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const bool has_seg = tail_r > 0 && (int)blockIdx.x < tail_r * tail_s;
+    const int seg_g = has_seg ? (int)blockIdx.x % tail_r : 0, seg_s = has_seg ? (int)blockIdx.x / tail_r : 0;
+    const uint32_t seg_cb0 = has_seg ? (uint32_t)((uint64_t)nck * seg_s / tail_s) : 0;
+    const uint32_t seg_cb1 = has_seg ? (uint32_t)((uint64_t)nck * (seg_s + 1) / tail_s) : 0;
+    const int64_t n_items = my_groups + (has_seg ? 1 : 0);
     // every thread advances the shared stage counter identically
-    const int64_t my_groups = (ngroups > (int64_t)blockIdx.x) ? (ngroups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    st.t = t_begin + (uint32_t)my_groups * nck;
+    st.t = t_begin + (uint32_t)my_groups * nck + (seg_cb1 - seg_cb0);
     if (warp == PRODUCER_WARP) {
         if (lane == 0) {
             // order the generic-proxy stores that produced x (before the last grid barrier)
             // ahead of the async-proxy reads below
             asm volatile("fence.proxy.async;" ::: "memory");
             uint32_t t = t_begin;
-            for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+            for (int64_t i = 0; i < n_items; ++i) {
+                const bool seg = i >= my_groups;
+                const int64_t g = seg ? g_main + seg_g : (int64_t)blockIdx.x + i * gridDim.x;
+                const uint32_t cb0 = seg ? seg_cb0 : 0, cb1 = seg ? seg_cb1 : nck;
                 const int row0 = (int)(g * TR);
-                for (uint32_t cb = 0; cb < nck; ++cb, ++t) {
+                for (uint32_t cb = cb0; cb < cb1; ++cb, ++t) {
                     const int col = (int)(cb * TCW);
                     const int64_t left = ncols - col;
                     const uint32_t xbytes = (uint32_t)((left < TCW ? left : TCW) * 8);
@@ -126,11 +158,14 @@ __device__ __forceinline__ void dense_pass_tma(const DenseView &dv, const double
             }
         }
     } else {
-        uint32_t t0 = t_begin;                   // stage number of column block 0 of the current group
+        uint32_t t0 = t_begin;                   // stage number of the first column block of the current item
         int buf = 0;
         const double *sp = &rp->P[warp][0][0];
         const double *sx = &rp->X[warp][0][0];
-        for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x, t0 += nck, buf ^= 1) {
+        for (int64_t i = 0; i < n_items; ++i, buf ^= 1) {
+            const bool seg = i >= my_groups;
+            const int64_t g = seg ? g_main + seg_g : (int64_t)blockIdx.x + i * gridDim.x;
+            const uint32_t cb0 = seg ? seg_cb0 : 0, cb1 = seg ? seg_cb1 : nck;
             const int64_t r0 = g * TR;
             const int nr = (int)(nloc - r0 < TR ? nloc - r0 : TR);
             double a[NX][TR][2];
@@ -139,8 +174,8 @@ __device__ __forceinline__ void dense_pass_tma(const DenseView &dv, const double
 #pragma unroll
                 for (int r = 0; r < TR; ++r) a[q][r][0] = a[q][r][1] = 0.0;
             // this warp's column blocks: those whose stage number is = warp (mod 8)
-            for (uint32_t cb = (uint32_t)(warp - (int)t0) & (TST - 1); cb < nck; cb += TST) {
-                const uint32_t t = t0 + cb;
+            for (uint32_t cb = cb0 + ((uint32_t)(warp - (int)t0) & (TST - 1)); cb < cb1; cb += TST) {
+                const uint32_t t = t0 + (cb - cb0);
                 const bool last = (cb + 1 == nck);
                 mbar_wait(&rp->full[warp], (t >> 3) & 1);
                 // lane takes columns 64k + 2 lane, k = 0..3, of all TR rows (conflict-free LDS.128)
@@ -170,6 +205,7 @@ __device__ __forceinline__ void dense_pass_tma(const DenseView &dv, const double
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&rp->empty[warp]);
             }
+            t0 += cb1 - cb0;
 #pragma unroll
             for (int q = 0; q < NX; ++q)
 #pragma unroll
@@ -180,14 +216,47 @@ __device__ __forceinline__ void dense_pass_tma(const DenseView &dv, const double
             // one barrier per group: part[] is double buffered, so the other warps run on into
             // the next group while warp 0's first lanes evaluate the epilogue (pow etc.)
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (threadIdx.x < nr) {
-                double s0 = 0.0, s1 = 0.0;
+            if (!seg) {
+                if (threadIdx.x < nr) {
+                    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                for (int w = 0; w < CONSUMER_WARPS; ++w) {
-                    s0 += rp->part[buf][w][0][threadIdx.x];
-                    if (NX > 1) s1 += rp->part[buf][w][NX - 1][threadIdx.x];
+                    for (int w = 0; w < CONSUMER_WARPS; ++w) {
+                        s0 += rp->part[buf][w][0][threadIdx.x];
+                        if (NX > 1) s1 += rp->part[buf][w][NX - 1][threadIdx.x];
+                    }
+                    epi(dv.row_begin + r0 + threadIdx.x, s0, NX > 1 ? s1 : s0);
                 }
-                epi(dv.row_begin + r0 + threadIdx.x, s0, NX > 1 ? s1 : s0);
+            } else if (warp == 0) {
+                // this CTA's segment of tail group seg_g: publish, count, and let the last arriver finish the rows
+                if (lane < TR) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int w = 0; w < CONSUMER_WARPS; ++w) {
+                        s0 += rp->part[buf][w][0][lane];
+                        if (NX > 1) s1 += rp->part[buf][w][NX - 1][lane];
+                    }
+                    double *slot = tail.buf + ((size_t)blockIdx.x * 2) * TR;
+                    __stcg(slot + lane, s0);
+                    if (NX > 1) __stcg(slot + TR + lane, s1);
+                    __threadfence();
+                }
+                __syncwarp();
+                unsigned int prev = 0;
+                if (lane == 0) prev = atomicAdd(tail.cnt + seg_g, 1u);
+                prev = __shfl_sync(0xffffffffu, prev, 0);
+                if (prev == (unsigned int)tail_s - 1) {
+                    __threadfence();
+                    if (lane < nr) {
+                        double s0 = 0.0, s1 = 0.0;
+                        for (int sgm = 0; sgm < tail_s; ++sgm) {               // segment order, whoever arrives last
+                            const double *slot = tail.buf + ((size_t)(sgm * tail_r + seg_g) * 2) * TR;
+                            s0 += __ldcg(slot + lane);
+                            if (NX > 1) s1 += __ldcg(slot + TR + lane);
+                        }
+                        epi(dv.row_begin + r0 + lane, s0, NX > 1 ? s1 : s0);
+                    }
+                    if (lane == 0) tail.cnt[seg_g] = 0;                        // every segment has arrived: ready for the next pass
+                }
             }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");   // part[] quiescent before the next pass
@@ -326,9 +395,9 @@ __device__ __forceinline__ void dense_pass_ldg(const DenseView &dv, const double
 // Dispatch on the operator's alignment class.
 template <int NX, class Epi>
 __device__ __forceinline__ void dense_pass(const DenseView &dv, const double *x0, const double *x1,
-                                           RowPipe<NX> *rp, PipeState &st, Epi &&epi) {
+                                           RowPipe<NX> *rp, PipeState &st, Epi &&epi, DenseTail tail = DenseTail{nullptr, nullptr}) {
     if (dv.vec2) {
-        dense_pass_tma<NX>(dv, x0, x1, rp, st, epi);
+        dense_pass_tma<NX>(dv, x0, x1, rp, st, epi, tail);
     } else {
         const int wg = blockIdx.x * SDFS_WARPS + (threadIdx.x >> 5);
         dense_pass_ldg<NX>(dv, x0, x1, wg, gridDim.x * SDFS_WARPS, epi);

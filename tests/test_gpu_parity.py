@@ -114,6 +114,34 @@ def test_from_dense_ragged_sizes(N):
                                rtol=1e-11, atol=1e-13)
 
 
+@pytest.mark.parametrize("extra_groups,ragged", [(13, 0), (18, 3), (70, 2), (1, 7)])
+def test_dense_last_wave_split(extra_groups, ragged):
+    """A row slab whose row groups leave a few groups for the last wave of the grid: the dense application cuts those
+    groups into column segments over all CTAs and combines them in segment order (rowdot.cuh, DenseTail; 70 extra groups
+    stay whole).  The slab is what one rank
+    of a row-sharded operator holds (north-star config 2 at 8 ranks leaves 13 of 1641 groups for a 12th wave)."""
+    sms = S.Context.default().device_info()["sm_count"]
+    N = 16400 + 2 * ragged
+    rows = (2 * sms + extra_groups) * 8 - ragged
+    rb = 40
+    rng = np.random.default_rng(extra_groups)
+    P = rng.random((rows, N))
+    P /= P.sum(1, keepdims=True)
+    a_row, a_col = 0.5 + rng.random(N), 0.5 + rng.random(N)
+    β, θ = 0.97, -3.7
+    w = 1.0 + 5 * rng.random(N)
+    op = S.WCOperator.from_dense(P, a_row, a_col, β, θ, row_range=(rb, rb + rows))
+    s = P @ (a_col * w**θ)
+    want = 1.0 + β * (a_row[rb:rb + rows] * s) ** (1.0 / θ)
+    for _ in range(3):                     # the arrival counters must be back at zero after every pass
+        got = np.asarray(op(w))[rb:rb + rows]
+        np.testing.assert_allclose(got, want, rtol=RTOL_T)
+    v = rng.standard_normal(N)
+    l = P @ (a_col * w**(θ - 1.0) * v)
+    want_j = β * a_row[rb:rb + rows] * (a_row[rb:rb + rows] * s) ** (1.0 / θ - 1.0) * l
+    np.testing.assert_allclose(np.asarray(op.jvp(w, v))[rb:rb + rows], want_j, rtol=1e-11, atol=1e-13)
+
+
 @pytest.mark.parametrize("N,ld", [(1001, 1002), (257, 320), (513, 514), (255, 256), (2, 2), (9, 16)])
 def test_from_dense_padded_leading_dimension(N, ld):
     """TMA path with N != ld: the padding columns hold NaN and must never be read as data
