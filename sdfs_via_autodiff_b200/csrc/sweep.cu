@@ -218,6 +218,38 @@ __global__ void k_state_vectors(int model, KronView kv, const double *__restrict
     }
 }
 
+// helpers of the register-blocked short-axis contraction (kron_mode_fibre2 below)
+static __host__ __device__ inline int kron_mode_nmats(const KronMode &md) {
+    int nm = 1;
+    for (int a = 0; a < md.nM; ++a) nm += (md.Mshape[a] - 1) * md.Mmat[a];
+    return nm;
+}
+static __host__ __device__ inline int fibre2_nmax(int n) { return n <= 4 ? 4 : (n <= 8 ? 8 : ((n + 1) & ~1)); }   // the NMAX instantiated for n
+static __host__ __device__ inline int fibre2_rb(int n) {
+    const int nmax = fibre2_nmax(n);
+    return nmax == 10 ? 5 : (nmax == 14 ? 7 : 4);
+}
+// doubles of shared memory the staged matrices of mode `md` need (0: axis too long for this path)
+static __host__ __device__ inline size_t fibre2_smat_doubles(const KronMode &md, int n) {
+    if (n > 16 || n < 2 || md.nout != n) return 0;
+    const int nmax = fibre2_nmax(n), rb = fibre2_rb(n);
+    const int rows = (n + rb - 1) / rb * rb;
+    return (size_t)kron_mode_nmats(md) * rows * nmax;
+}
+#define FIBRE2_SMAT_MAX 2048          // 16 KB of staged matrices at most (SSY (10,)^4: 13 x 100 doubles for all four modes)
+// all modes of the view staged side by side (mode m at offset sum of the modes before it): total doubles, 0 when some
+// mode does not qualify or the total exceeds the budget - then modes are staged one at a time
+static __host__ __device__ inline size_t fibre2_all_doubles(const KronView &kv) {
+    size_t tot = 0;
+    for (int m = 0; m < kv.n_modes; ++m) {
+        const size_t need = fibre2_smat_doubles(kv.modes[m], kv.shape[kv.modes[m].dim]);
+        if (need == 0) return 0;
+        tot += need;
+    }
+    return tot <= FIBRE2_SMAT_MAX ? tot : 0;
+}
+
+
 // dynamic shared memory of k_sweep_fused: the resident N-vector + the largest factor matrix the lean
 // contraction variants stage (rows 8 IT, pitch 8 IT + 4 with IT = 2, 4, 6, 8; 8 x 8 for the FMA kernel).
 // Axes longer than 64 use the cached-load pass, which is not in-place safe: no fused path (returns 0).
@@ -233,6 +265,12 @@ static inline size_t sweep_fused_smem(const KronView &kv) {
             if (need > smat) smat = need;
         }
     }
+    // short axes: all matrices of a mode staged at once for kron_mode_fibre2 (when they fit the budget)
+    for (int m = 0; m < kv.n_modes; ++m) {
+        const size_t need = fibre2_smat_doubles(kv.modes[m], kv.shape[kv.modes[m].dim]);
+        if (need <= FIBRE2_SMAT_MAX && need > smat) smat = need;
+    }
+    if (fibre2_all_doubles(kv) > smat) smat = fibre2_all_doubles(kv);       // ... of all modes side by side
     return (size_t)(sweep_fused_ldn(kv.N) + smat) * sizeof(double);
 }
 
@@ -447,10 +485,108 @@ static int sweep_factor(sdfs_op *op, SweepWork &w, int64_t B, const double *V, c
 // once per application instead of once per mode; two CTAs per SM overlap one column's global loads with
 // the other's contractions.  Columns that have converged (SA) cost one copy.
 // ---------------------------------------------------------------------------
+// Short axes (n <= 16) on a vector resident in shared memory: register-blocked FMA contraction, two fibres per thread.
+// A thread loads both fibres into registers (so the contraction is in place: nobody else touches these fibres), then
+// forms RB output rows at a time: every matrix element fetched (LDS.128, the same address across the warp while its
+// fibres share a matrix) feeds two FMAs per fibre - 2 x NMAX x RB FMAs per NMAX x RB / 2 shared-memory loads, which puts
+// the loop on the fp64 pipe instead of the shared-memory pipe (kron_mode_fibre: one fibre per thread, rows padded to 4 and
+// columns to 16, one matrix per work item with two block barriers each - 14 clocks per fibre per SM at n = 10).
+// ALL matrices of the mode are staged once (row pitch NMAX, rows padded to a multiple of RB with zeros), so the
+// whole mode is one pass over the fibres without block barriers inside.
+// Fibre pairs: thread t takes fibres q and q + ceil(F / 2) of one matrix combination, so neighbouring threads read
+// neighbouring fibres (conflict-free for every mode but the innermost axis, 4-way there).
+// stage every matrix of the mode: row pitch NMAX, rows padded to a multiple of RB, zeros outside n x n
+__device__ __forceinline__ void fibre2_stage(const KronMode &md, int n, double *smat) {
+    const int NMAX = fibre2_nmax(n), RB = fibre2_rb(n);
+    const int rows = (n + RB - 1) / RB * RB;
+    const int msz = rows * NMAX;
+    const int nmats = kron_mode_nmats(md);
+    for (int e = threadIdx.x; e < nmats * msz; e += blockDim.x) {
+        const int mt = e / msz, r = e - mt * msz, i = r / NMAX, j = r - i * NMAX;
+        double v = 0.0;
+        if (i < n && j < n) {
+            v = md.mat[((long long)mt * n + i) * n + j];
+            if (md.colscale) v *= md.colscale[j];
+        }
+        smat[e] = v;
+    }
+}
+
+template <int NMAX, int RB>
+__device__ __forceinline__ void kron_mode_fibre2(const KronMode &md, int n, double *cur, const double *smat) {
+    const int rows = (n + RB - 1) / RB * RB;
+    const int msz = rows * NMAX;
+    const unsigned F = (unsigned)md.Fcount, half = (F + 1) >> 1;
+    const unsigned pairs = (unsigned)md.Mcount * half;
+    const int stride = (int)md.stride;            // the vector lives in shared memory: 32-bit element indices
+    for (unsigned q = threadIdx.x; q < pairs; q += blockDim.x) {
+        const unsigned mc = q / half, f0 = q - mc * half, f1 = f0 + half;
+        unsigned rem = mc;
+        int mbase = (int)md.base_off;
+        int mat = 0;
+        for (int a = md.nM - 1; a >= 0; --a) {
+            const unsigned sh = (unsigned)md.Mshape[a], c = rem % sh;
+            rem /= sh;
+            mat += (int)c * md.Mmat[a];
+            mbase += (int)c * (int)md.Mstride[a];
+        }
+        int b0 = mbase, b1 = mbase;
+        unsigned r0 = f0, r1 = f1 < F ? f1 : f0;
+        for (int a = md.nF - 1; a >= 0; --a) {
+            const unsigned sh = (unsigned)md.Fshape[a];
+            const unsigned c0 = r0 % sh, c1 = r1 % sh;
+            r0 /= sh; r1 /= sh;
+            b0 += (int)c0 * (int)md.Fstride[a];
+            b1 += (int)c1 * (int)md.Fstride[a];
+        }
+        const bool two = f1 < F;
+        double x0[NMAX], x1[NMAX];
+        double *p0 = cur + b0, *p1 = cur + b1;
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+            x0[j] = (j < n) ? p0[j * stride] : 0.0;
+            x1[j] = (j < n) ? p1[j * stride] : 0.0;
+        }
+        const double2 *mrow = reinterpret_cast<const double2 *>(smat + mat * msz);
+        for (int rb = 0; rb < rows; rb += RB) {
+            double a0[RB], a1[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) a0[r] = a1[r] = 0.0;
+#pragma unroll
+            for (int j = 0; j < NMAX / 2; ++j) {
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const double2 mm = mrow[(rb + r) * (NMAX / 2) + j];
+                    a0[r] = fma(mm.x, x0[2 * j], a0[r]); a1[r] = fma(mm.x, x1[2 * j], a1[r]);
+                    a0[r] = fma(mm.y, x0[2 * j + 1], a0[r]); a1[r] = fma(mm.y, x1[2 * j + 1], a1[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RB; ++r)
+                if (rb + r < n) {
+                    p0[(rb + r) * stride] = a0[r];
+                    if (two) p1[(rb + r) * stride] = a1[r];
+                }
+        }
+    }
+}
+
+// one mode of the resident vector on the register-blocked FMA path (matrices already staged at `smat`)
+__device__ __forceinline__ void fibre2_dispatch(const KronMode &md, int n, double *cur, const double *smat) {
+    switch (fibre2_nmax(n)) {
+    case 4: kron_mode_fibre2<4, 4>(md, n, cur, smat); break;
+    case 8: kron_mode_fibre2<8, 4>(md, n, cur, smat); break;
+    case 10: kron_mode_fibre2<10, 5>(md, n, cur, smat); break;
+    case 12: kron_mode_fibre2<12, 4>(md, n, cur, smat); break;
+    case 14: kron_mode_fibre2<14, 7>(md, n, cur, smat); break;
+    default: kron_mode_fibre2<16, 4>(md, n, cur, smat); break;
+    }
+}
+
 #define SWF_THREADS 256
 #define SWF_UNROLL 8            // independent global loads in flight per thread in the load / epilogue loops
 __global__ void __launch_bounds__(SWF_THREADS, 2)
-k_sweep_fused(const __grid_constant__ KronView kv, int64_t ldw, int64_t ldn, const double *__restrict__ in_panel, int prologue,
+k_sweep_fused(const __grid_constant__ KronView kv, int64_t ldw, int64_t ldn, const double *__restrict__ in_panel, int prologue, int fibre2,
               const double *__restrict__ h_lam, const double *__restrict__ sig_c, const double *__restrict__ mz,
               SweepEpi ep, SweepCols sc) {
     extern __shared__ __align__(16) double fsm[];
@@ -465,39 +601,119 @@ k_sweep_fused(const __grid_constant__ KronView kv, int64_t ldw, int64_t ldn, con
         return;
     }
     const double *col = in_panel + b * ldw;
-    for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {
-        double v[SWF_UNROLL], h[SWF_UNROLL];
-#pragma unroll
-        for (int u = 0; u < SWF_UNROLL; ++u) {
-            const int64_t n = n0 + (int64_t)u * blockDim.x;
-            v[u] = n < N ? col[n] : 1.0;
-            h[u] = (prologue && n < N) ? h_lam[n] : 0.0;
+    // plain column load (every Krylov mat-vec): ONE bulk async copy, all of the column in flight at once, completing on
+    // an mbarrier while the threads stage the factor matrices.  The streams the epilogue will read are prefetched into
+    // L2 meanwhile (they are consumed ~20 us later, after the contractions).
+    __shared__ uint64_t col_bar;
+    const uint32_t col_bytes = (uint32_t)(ldn * sizeof(double));          // even element count; the panel pitch covers it
+    const bool bulk = !prologue && (((uintptr_t)col | (uintptr_t)cur) & 15) == 0 && ldn <= ldw;
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&col_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(&col_bar, col_bytes);
+            bulk_g2s(cur, col, col_bytes, &col_bar);
+            const uint32_t pf = (uint32_t)((N * sizeof(double)) & ~(size_t)15);
+            if (pf) {
+                if (ep.mode == 2) {
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.D + b * ldw), "r"(pf) : "memory");
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.Vsub + b * ldw), "r"(pf) : "memory");
+                } else {
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ep.W + b * ldw), "r"(pf) : "memory");
+                }
+            }
         }
+    } else {
+        for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {
+            double v[SWF_UNROLL], h[SWF_UNROLL];
 #pragma unroll
-        for (int u = 0; u < SWF_UNROLL; ++u) {
-            const int64_t n = n0 + (int64_t)u * blockDim.x;
-            if (n < N) cur[n] = prologue ? exp(th * (h[u] + log(v[u]))) : v[u];   // exp(theta h) w^theta, as k_sweep_prologue
+            for (int u = 0; u < SWF_UNROLL; ++u) {
+                const int64_t n = n0 + (int64_t)u * blockDim.x;
+                v[u] = n < N ? col[n] : 1.0;
+                h[u] = (prologue && n < N) ? h_lam[n] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < SWF_UNROLL; ++u) {
+                const int64_t n = n0 + (int64_t)u * blockDim.x;
+                if (n < N) cur[n] = prologue ? exp(th * (h[u] + log(v[u]))) : v[u];   // exp(theta h) w^theta, as k_sweep_prologue
+            }
         }
     }
-    __syncthreads();
-    for (int m = 0; m < kv.n_modes; ++m) {
-        kron_mode_apply<false, true>(kv, m, cur, smat, [&](int64_t idx, double s) { cur[idx] = s; }, KronShare(0, 1));
-        __syncthreads();
+    // short axes throughout: the matrices of all modes are staged now, next to the column load, and every mode is
+    // one pass over its fibres with a single block barrier behind it
+    const bool all_staged = fibre2 && fibre2_all_doubles(kv) > 0;
+    if (all_staged) {
+        double *sm = smat;
+        for (int m = 0; m < kv.n_modes; ++m) {
+            const int n = kv.shape[kv.modes[m].dim];
+            fibre2_stage(kv.modes[m], n, sm);
+            sm += fibre2_smat_doubles(kv.modes[m], n);
+        }
+    }
+    __syncthreads();                    // staged matrices (and, for thread 0's barrier init, the barrier itself) visible
+    if (bulk) mbar_wait(&col_bar, 0);   // the column has landed
+    {
+        const double *sm = smat;
+        for (int m = 0; m < kv.n_modes; ++m) {
+            const KronMode &md = kv.modes[m];
+            const int n = kv.shape[md.dim];
+            const size_t need = fibre2 ? fibre2_smat_doubles(md, n) : 0;
+            if (all_staged) {
+                fibre2_dispatch(md, n, cur, sm);
+                sm += need;
+            } else if (need > 0 && need <= FIBRE2_SMAT_MAX) {
+                fibre2_stage(md, n, smat);
+                __syncthreads();
+                fibre2_dispatch(md, n, cur, smat);
+            } else {
+                kron_mode_apply<false, true>(kv, m, cur, smat, [&](int64_t idx, double s) { cur[idx] = s; }, KronShare(0, 1));
+            }
+            __syncthreads();
+        }
     }
     // epilogue on the resident contraction (same arithmetic as k_sweep_epi_ew)
     if (ep.mode == 2) {
+        const double *Db = ep.D + b * ldw, *Vb = ep.Vsub + b * ldw;
+        double *Ob = ep.out0 + b * ldw;
+        if (((((uintptr_t)Db) | ((uintptr_t)Vb) | ((uintptr_t)Ob)) & 15) == 0) {
+            // 16-byte accesses, SWF_UNROLL / 2 x 2 loads of each stream in flight per thread
+            const int64_t N2 = N >> 1;
+            const double2 *D2 = reinterpret_cast<const double2 *>(Db), *V2 = reinterpret_cast<const double2 *>(Vb);
+            const double2 *C2 = reinterpret_cast<const double2 *>(cur);
+            double2 *O2 = reinterpret_cast<double2 *>(Ob);
+            constexpr int U2 = SWF_UNROLL / 2;
+            for (int64_t n0 = threadIdx.x; n0 < N2; n0 += (int64_t)U2 * blockDim.x) {
+                double2 d[U2], vs[U2];
+#pragma unroll
+                for (int u = 0; u < U2; ++u) {
+                    const int64_t n = n0 + (int64_t)u * blockDim.x;
+                    d[u] = n < N2 ? D2[n] : make_double2(0.0, 0.0);
+                    vs[u] = n < N2 ? V2[n] : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < U2; ++u) {
+                    const int64_t n = n0 + (int64_t)u * blockDim.x;
+                    if (n < N2) {
+                        const double2 c = C2[n];
+                        O2[n] = make_double2(d[u].x * c.x - vs[u].x, d[u].y * c.y - vs[u].y);
+                    }
+                }
+            }
+            if ((N & 1) && threadIdx.x == 0) Ob[N - 1] = Db[N - 1] * cur[N - 1] - Vb[N - 1];
+            return;
+        }
         for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {
             double d[SWF_UNROLL], vs[SWF_UNROLL];
 #pragma unroll
             for (int u = 0; u < SWF_UNROLL; ++u) {
                 const int64_t n = n0 + (int64_t)u * blockDim.x;
-                d[u] = n < N ? ep.D[b * ldw + n] : 0.0;
-                vs[u] = n < N ? ep.Vsub[b * ldw + n] : 0.0;
+                d[u] = n < N ? Db[n] : 0.0;
+                vs[u] = n < N ? Vb[n] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < SWF_UNROLL; ++u) {
                 const int64_t n = n0 + (int64_t)u * blockDim.x;
-                if (n < N) ep.out0[b * ldw + n] = d[u] * cur[n] - vs[u];
+                if (n < N) Ob[n] = d[u] * cur[n] - vs[u];
             }
         }
         return;
@@ -556,7 +772,9 @@ static int sweep_fused(sdfs_op *op, SweepWork &w, int64_t B, const double *in_pa
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const bool prof = ctx->prof_on && ctx->prof_used + 2 <= ctx->prof_ev.size();
     if (prof) CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
-    k_sweep_fused<<<(unsigned)B, SWF_THREADS, smem, ctx->stream>>>(op->kv, w.ldw, sweep_fused_ldn(op->kv.N), in_panel, prologue, w.hl, w.sc,
+    // SDFS_SWEEP_FIBRE2=0: the round-1 thread-per-fibre contraction for short axes (A/B switch)
+    static const int fibre2 = !(getenv("SDFS_SWEEP_FIBRE2") && atoi(getenv("SDFS_SWEEP_FIBRE2")) == 0);
+    k_sweep_fused<<<(unsigned)B, SWF_THREADS, smem, ctx->stream>>>(op->kv, w.ldw, sweep_fused_ldn(op->kv.N), in_panel, prologue, fibre2, w.hl, w.sc,
                                                                   w.mz, ep, sc);
     if (prof) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));

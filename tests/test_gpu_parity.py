@@ -910,7 +910,8 @@ def test_factor_form_large_axes_every_tile_count_vs_oracle():
 
 
 @pytest.mark.parametrize("model,shapes", [("ssy", (4, 7, 6, 5)), ("ssy", (13, 5, 14, 3)), ("gcy", (2, 3, 2, 3, 2, 3)),
-                                          ("ssy", (20, 3, 18, 2)), ("ssy", (40, 2, 3, 33))])
+                                          ("ssy", (20, 3, 18, 2)), ("ssy", (40, 2, 3, 33)),
+                                          ("ssy", (9, 10, 11, 12)), ("ssy", (16, 15, 4, 13))])
 def test_sweep_factor_form_matches_dense_form_and_oracle(model, shapes):
     """form="factor" (Markov factors contracted mode by mode for all columns at once, no P stored)
     against form="dense" (the tensor-core GEMM) and the oracle: T panel, per-column SA counts,
