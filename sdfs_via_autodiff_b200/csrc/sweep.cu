@@ -1061,6 +1061,184 @@ __global__ void k_swn_phase5(int64_t N, int64_t ldw, long long maxiter, SwnState
     }
 }
 
+// ---------------------------------------------------------------------------
+// The whole inner BiCGSTAB solve of one column in ONE CTA (grids whose column fits in shared memory and whose axes
+// are all short: the k_sweep_fused / kron_mode_fibre2 case).  A column's Krylov iteration needs nothing from the
+// other columns, and the CTA that contracts a column already holds all of it, so phases 1, 3 and 5 above run as
+// loops of the same CTA around the two resident contractions, their dot products as block reductions: no launch
+// boundaries, no host polls, the factor matrices staged once per solve, and the mat-vec input / the vectors q and t
+// never travel through global memory (q is stored once for the next iteration's p update, t not at all).
+// Same arithmetic per element and the same per-thread accumulation order as k_swn_phase1/3/5 + k_sweep_fused
+// (256 threads, element n on thread n mod 256, partials in n order), so every scalar - and with it every
+// column's iteration count - is bit-identical to the phase-kernel path.
+// ---------------------------------------------------------------------------
+#define SWI_U 4
+__global__ void __launch_bounds__(SWF_THREADS, 2)
+k_swn_inner_fused(const __grid_constant__ KronView kv, int64_t ldw, int64_t ldn, long long maxiter, SwnState st, SwnPanels p,
+                  int *max_k) {
+    extern __shared__ __align__(16) double fsm[];
+    __shared__ double sm[SWN_THREADS / 32];
+    static_assert(SWF_THREADS == SWN_THREADS, "the column loops assume the phase kernels' thread count");
+    const int64_t N = kv.N;
+    const int64_t b = blockIdx.x;
+    if (!st.in_active[b]) return;
+    double *cur = fsm, *smat = fsm + ldn;
+    {
+        double *sm_m = smat;
+        for (int m = 0; m < kv.n_modes; ++m) {
+            const int n = kv.shape[kv.modes[m].dim];
+            fibre2_stage(kv.modes[m], n, sm_m);
+            sm_m += fibre2_smat_doubles(kv.modes[m], n);
+        }
+    }
+    const double *R = p.R + b * ldw, *Rh = p.Rh + b * ldw, *C = p.C + b * ldw, *D = p.D + b * ldw;
+    double *Rw = p.R + b * ldw, *Pv = p.Pv + b * ldw, *Q = p.Q + b * ldw, *Sv = p.Sv + b * ldw, *X = p.X + b * ldw;
+    double rho = st.rho[b], alpha = st.alpha[b], omega = st.omega[b], rho_next = st.rho_next[b], rs = st.rs[b];
+    const double atol2 = st.atol2[b];
+    long long k = st.k[b];
+    const int64_t step = (int64_t)SWI_U * SWN_THREADS;
+    auto contract = [&]() {
+        const double *sm_m = smat;
+        __syncthreads();
+        for (int m = 0; m < kv.n_modes; ++m) {
+            const KronMode &md = kv.modes[m];
+            const int n = kv.shape[md.dim];
+            fibre2_dispatch(md, n, cur, sm_m);
+            sm_m += fibre2_smat_doubles(md, n);
+            __syncthreads();
+        }
+    };
+    for (;;) {
+        // ---- phase 1: p = r + beta (p - omega q); mat-vec input c .* p
+        const double beta = rho_next / rho * alpha / omega;
+        for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {
+            double r[SWI_U], pv[SWI_U], q[SWI_U], c[SWI_U];
+#pragma unroll
+            for (int u = 0; u < SWI_U; ++u) {
+                const int64_t n = n0 + (int64_t)u * SWN_THREADS;
+                if (n < N) { r[u] = R[n]; pv[u] = Pv[n]; q[u] = Q[n]; c[u] = C[n]; }
+            }
+#pragma unroll
+            for (int u = 0; u < SWI_U; ++u) {
+                const int64_t n = n0 + (int64_t)u * SWN_THREADS;
+                if (n < N) {
+                    const double pn = r[u] + beta * (pv[u] - omega * q[u]);
+                    Pv[n] = pn;
+                    cur[n] = c[u] * pn;
+                }
+            }
+        }
+        contract();
+        // ---- q = d .* S - p (the Krylov epilogue of k_sweep_fused), <rhat, q>
+        double acc = 0.0;
+        for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {
+            double d[SWI_U], pv[SWI_U], rh[SWI_U];
+#pragma unroll
+            for (int u = 0; u < SWI_U; ++u) {
+                const int64_t n = n0 + (int64_t)u * SWN_THREADS;
+                if (n < N) { d[u] = D[n]; pv[u] = Pv[n]; rh[u] = Rh[n]; }
+            }
+#pragma unroll
+            for (int u = 0; u < SWI_U; ++u) {
+                const int64_t n = n0 + (int64_t)u * SWN_THREADS;
+                if (n < N) {
+                    const double qn = d[u] * cur[n] - pv[u];
+                    Q[n] = qn;
+                    cur[n] = qn;
+                    acc += rh[u] * qn;
+                }
+            }
+        }
+        const double rq = cta_reduce_sum(acc, sm);
+        // ---- phase 3: alpha, s = r - alpha q, <s, s>, mat-vec input c .* s
+        const double alpha_ = rho_next / rq;
+        double ss = 0.0;
+        for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {
+            double r[SWI_U], c[SWI_U];
+#pragma unroll
+            for (int u = 0; u < SWI_U; ++u) {
+                const int64_t n = n0 + (int64_t)u * SWN_THREADS;
+                if (n < N) { r[u] = R[n]; c[u] = C[n]; }
+            }
+#pragma unroll
+            for (int u = 0; u < SWI_U; ++u) {
+                const int64_t n = n0 + (int64_t)u * SWN_THREADS;
+                if (n < N) {
+                    const double sn = r[u] - alpha_ * cur[n];
+                    Sv[n] = sn;
+                    cur[n] = c[u] * sn;
+                    ss += sn * sn;
+                }
+            }
+        }
+        ss = cta_reduce_sum(ss, sm);
+        const int early = (ss < atol2) ? 1 : 0;
+        contract();
+        // ---- t = d .* S - s (kept in shared memory only), <t, s>, <t, t>
+        double ts = 0.0, tt = 0.0;
+        for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {
+            double d[SWI_U], sv[SWI_U];
+#pragma unroll
+            for (int u = 0; u < SWI_U; ++u) {
+                const int64_t n = n0 + (int64_t)u * SWN_THREADS;
+                if (n < N) { d[u] = D[n]; sv[u] = Sv[n]; }
+            }
+#pragma unroll
+            for (int u = 0; u < SWI_U; ++u) {
+                const int64_t n = n0 + (int64_t)u * SWN_THREADS;
+                if (n < N) {
+                    const double tn = d[u] * cur[n] - sv[u];
+                    cur[n] = tn;
+                    ts += tn * sv[u];
+                    tt += tn * tn;
+                }
+            }
+        }
+        ts = cta_reduce_sum(ts, sm);
+        tt = cta_reduce_sum(tt, sm);
+        // ---- phase 5: omega, x and r updates, <r, r>, <rhat, r>, loop condition
+        const double omega_ = ts / tt;
+        double rr = 0.0, rhr = 0.0;
+        for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {
+            double pv[SWI_U], sv[SWI_U], x[SWI_U], rh[SWI_U];
+#pragma unroll
+            for (int u = 0; u < SWI_U; ++u) {
+                const int64_t n = n0 + (int64_t)u * SWN_THREADS;
+                if (n < N) { pv[u] = Pv[n]; sv[u] = Sv[n]; x[u] = X[n]; rh[u] = Rh[n]; }
+            }
+#pragma unroll
+            for (int u = 0; u < SWI_U; ++u) {
+                const int64_t n = n0 + (int64_t)u * SWN_THREADS;
+                if (n < N) {
+                    double xn, rn;
+                    if (early) { xn = x[u] + alpha_ * pv[u]; rn = sv[u]; }
+                    else { xn = x[u] + (alpha_ * pv[u] + omega_ * sv[u]); rn = sv[u] - omega_ * cur[n]; }
+                    X[n] = xn;
+                    Rw[n] = rn;
+                    rr += rn * rn;
+                    rhr += rh[u] * rn;
+                }
+            }
+        }
+        rr = cta_reduce_sum(rr, sm);
+        rhr = cta_reduce_sum(rhr, sm);
+        const double rho_ = rho_next;
+        long long k_ = (omega_ == 0.0 || alpha_ == 0.0) ? -11 : k + 1;
+        if (rho_ == 0.0) k_ = -10;
+        k = k_; omega = omega_; alpha = alpha_; rho = rho_; rs = rr; rho_next = rhr;
+        if (!(rr > atol2 && k_ < maxiter && k_ >= 0)) break;
+        __syncthreads();            // this iteration's stores to r, p, q are read by other threads' elements? no: same thread per
+                                    // element throughout; the barrier only keeps `cur` reuse ordered for the next phase 1
+    }
+    if (threadIdx.x == 0) {
+        st.k[b] = k; st.omega[b] = omega; st.alpha[b] = alpha; st.rho[b] = rho; st.rs[b] = rs; st.rho_next[b] = rho_next;
+        st.in_active[b] = 0;
+        st.inner_total[b] += (k > 0 ? k : 0);
+        atomicSub(st.n_in_active, 1);
+        atomicMax(max_k, (int)(k > 0 ? k : 1));
+    }
+}
+
 // w <- w - x ; error = max|x| ; outer loop condition (successive_approx rule, solvers.py:34-40)
 __global__ void k_swn_outer(int64_t N, int64_t ldw, double tol, long long max_iter, SwnState st, SwnPanels p) {
     __shared__ double sm[SWN_THREADS / 32];
@@ -1113,10 +1291,10 @@ extern "C" int sdfs_sweep_solve_newton(sdfs_op *op, const double *h_prefs, int64
         if (e == cudaSuccess) e = cudaMemsetAsync(pan, 0, 12 * pdoubles * sizeof(double), ctx->stream);
         if (e == cudaSuccess) e = cudaMallocAsync(&sca, 7 * B * sizeof(double), ctx->stream);
         if (e == cudaSuccess) e = cudaMallocAsync(&lls, 3 * B * sizeof(long long), ctx->stream);
-        if (e == cudaSuccess) e = cudaMallocAsync(&ints, (3 * B + 2) * sizeof(int), ctx->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&ints, (3 * B + 3) * sizeof(int), ctx->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(sca, 0, 7 * B * sizeof(double), ctx->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(lls, 0, 3 * B * sizeof(long long), ctx->stream);
-        if (e == cudaSuccess) e = cudaMemsetAsync(ints, 0, (3 * B + 2) * sizeof(int), ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ints, 0, (3 * B + 3) * sizeof(int), ctx->stream);
         if (e != cudaSuccess) rc = sdfs_set_error(ctx, SDFS_ERR_NOMEM, "sweep newton workspace (%.2f GB): %s", 12 * pdoubles * 8 / 1e9, cudaGetErrorString(e));
     }
     if (rc == SDFS_OK) {
@@ -1134,6 +1312,13 @@ extern "C" int sdfs_sweep_solve_newton(sdfs_op *op, const double *h_prefs, int64
         cudaMemcpyAsync(st.n_out_active, &nb, 4, cudaMemcpyHostToDevice, ctx->stream);
         ctx->launches += 2;
         SweepCols sc{w.gamma, w.theta, w.beta, nullptr};
+        // SDFS_SWEEP_INNER_FUSED=0: Krylov phases as separate launches over all columns (round 1; the A/B switch)
+        static const bool inner_allowed = !(getenv("SDFS_SWEEP_INNER_FUSED") && atoi(getenv("SDFS_SWEEP_INNER_FUSED")) == 0) &&
+                                          !(getenv("SDFS_SWEEP_FIBRE2") && atoi(getenv("SDFS_SWEEP_FIBRE2")) == 0);
+        const bool inner_fused = inner_allowed && w.fused && fibre2_all_doubles(op->kv) > 0;
+        const size_t fused_smem = sweep_fused_smem(op->kv);
+        if (inner_fused)
+            cudaFuncSetAttribute(k_swn_inner_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem);
         int n_out = nb;
         auto read_int = [&](const int *d, int *h) -> int {
             cudaError_t e = cudaMemcpyAsync(h, d, 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1151,6 +1336,21 @@ extern "C" int sdfs_sweep_solve_newton(sdfs_op *op, const double *h_prefs, int64
             k_swn_init<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, rtol, atol, st, p);
             ctx->launches += 2;
             int n_in = 0;
+            if (inner_fused) {
+                // every column's whole Krylov solve in one launch (one CTA per column); the application count reported
+                // is that of the column that iterated longest
+                int *max_k = ints + 3 * B + 2;
+                cudaMemsetAsync(max_k, 0, 4, ctx->stream);
+                k_swn_inner_fused<<<bgrid, SWF_THREADS, fused_smem, ctx->stream>>>(op->kv, w.ldw, sweep_fused_ldn(N), kmax, st, p, max_k);
+                ctx->launches++;
+                int mk = 0;
+                rc = read_int(max_k, &mk);
+                gemms += 2 * (int64_t)mk;
+                if (rc == SDFS_OK) {
+                    cudaError_t le = cudaGetLastError();
+                    if (le != cudaSuccess) rc = sdfs_set_error(ctx, SDFS_ERR_CUDA, "sweep newton (fused Krylov): %s", cudaGetErrorString(le));
+                }
+            } else {
             rc = read_int(st.n_in_active, &n_in);
             while (rc == SDFS_OK && n_in > 0) {
                 k_swn_phase1<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, st, p);
@@ -1165,6 +1365,7 @@ extern "C" int sdfs_sweep_solve_newton(sdfs_op *op, const double *h_prefs, int64
                 ctx->launches += 3;
                 gemms += 2;
                 rc = read_int(st.n_in_active, &n_in);     // 4-byte poll per Krylov iteration (>= 10 ms of GEMM each)
+            }
             }
             if (rc) break;
             k_swn_outer<<<bgrid, SWN_THREADS, 0, ctx->stream>>>(N, w.ldw, tol, (long long)max_iter, st, p);
