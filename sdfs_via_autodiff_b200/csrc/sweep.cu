@@ -818,6 +818,10 @@ __global__ void k_copy_panel(const double *src, int64_t lds, double *dst, int64_
         dst[(e / N) * ldd + e % N] = src[(e / N) * lds + e % N];
 }
 
+// successive approximation of every column inside one CTA (defined next to the Newton sweep's fused inner solve)
+static bool sweep_sa_cols_applicable(const sdfs_op *op, const SweepWork &w);
+static int sweep_sa_cols(sdfs_op *op, SweepWork &w, int64_t B, double *W, double tol, long long max_iter);
+
 extern "C" {
 
 int sdfs_sweep_set_form(sdfs_op *op, int form) {
@@ -868,6 +872,10 @@ int sdfs_sweep_solve_sa(sdfs_op *op, const double *h_prefs, int64_t B, double w_
         ctx->launches++;
         int active = (int)B;
         int64_t steps = 0;
+        if (max_iter > 0 && sweep_sa_cols_applicable(op, w)) {
+            rc = sweep_sa_cols(op, w, B, cur, tol, (long long)max_iter);      // in place: `cur` holds the fixed points
+            active = 0;
+        }
         while (rc == SDFS_OK && active > 0 && steps < max_iter) {
             // a burst of steps with no host synchronisation; convergence is tracked on the device
             for (int i = 0; i < 64 && steps < max_iter && rc == SDFS_OK; ++i, ++steps) {
@@ -1237,6 +1245,125 @@ k_swn_inner_fused(const __grid_constant__ KronView kv, int64_t ldw, int64_t ldn,
         atomicSub(st.n_in_active, 1);
         atomicMax(max_k, (int)(k > 0 ? k : 1));
     }
+}
+
+// ---------------------------------------------------------------------------
+// Successive approximation of one column in ONE CTA, all iterations (solvers.py:19-48 per column): the same case as
+// k_swn_inner_fused (column in shared memory, short axes).  Per step: the resident contractions, then one loop that
+// evaluates the epilogue y = 1 + beta exp((log S + log a_row) / theta), the error against the stored w, stores y and
+// writes the NEXT step's contraction input exp(theta (h_lambda + log y)) straight back into shared memory - the
+// arithmetic of k_sweep_fused's epilogue and prologue, element by element, so iterates, errors and iteration counts are
+// bit-identical to the launch-per-step path.  No launches, no host polls, no panel round trips: a step reads w (its own
+// 80 KB, L2-resident) and the three state vectors, and writes w.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(SWF_THREADS, 2)
+k_sweep_sa_col(const __grid_constant__ KronView kv, int64_t ldw, int64_t ldn, double *__restrict__ W,
+               const double *__restrict__ h_lam, const double *__restrict__ sig_c, const double *__restrict__ mz,
+               SweepCols sc, double tol, long long max_iter, long long *iters, double *last_err) {
+    extern __shared__ __align__(16) double fsm[];
+    __shared__ double red[SWF_THREADS / 32];
+    const int64_t N = kv.N;
+    const int64_t b = blockIdx.x;
+    double *cur = fsm, *smat = fsm + ldn;
+    {
+        double *sm_m = smat;
+        for (int m = 0; m < kv.n_modes; ++m) {
+            const int n = kv.shape[kv.modes[m].dim];
+            fibre2_stage(kv.modes[m], n, sm_m);
+            sm_m += fibre2_smat_doubles(kv.modes[m], n);
+        }
+    }
+    const double th = sc.theta[b], g = sc.gamma[b], be = sc.beta[b];
+    const double omg = 1.0 - g, inv_th = 1.0 / th;
+    double *Wb = W + b * ldw;
+    constexpr int U = 4;
+    const int64_t step = (int64_t)U * SWF_THREADS;
+    for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {          // first contraction input from the stored w
+        double v[U], h[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t n = n0 + (int64_t)u * SWF_THREADS;
+            v[u] = n < N ? Wb[n] : 1.0;
+            h[u] = n < N ? h_lam[n] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t n = n0 + (int64_t)u * SWF_THREADS;
+            if (n < N) cur[n] = exp(th * (h[u] + log(v[u])));
+        }
+    }
+    long long it = 0;
+    double e = 0.0;
+    for (;;) {
+        {
+            const double *sm_m = smat;
+            __syncthreads();
+            for (int m = 0; m < kv.n_modes; ++m) {
+                const KronMode &md = kv.modes[m];
+                const int n = kv.shape[md.dim];
+                fibre2_dispatch(md, n, cur, sm_m);
+                sm_m += fibre2_smat_doubles(md, n);
+                __syncthreads();
+            }
+        }
+        double emax = 0.0;
+        for (int64_t n0 = threadIdx.x; n0 < N; n0 += step) {
+            double wo[U], sg[U], zz[U], h[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t n = n0 + (int64_t)u * SWF_THREADS;
+                wo[u] = n < N ? Wb[n] : 0.0;
+                sg[u] = n < N ? sig_c[n] : 0.0;
+                zz[u] = n < N ? mz[n] : 0.0;
+                h[u] = n < N ? h_lam[n] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t n = n0 + (int64_t)u * SWF_THREADS;
+                if (n >= N) continue;
+                const double t2 = omg * sg[u];
+                const double la = 0.5 * (t2 * t2) + omg * zz[u];
+                const double ls = log(cur[n]) + la;
+                const double y = 1.0 + be * exp(inv_th * ls);
+                Wb[n] = y;
+                const double dd = fabs(y - wo[u]);
+                emax = (dd != dd || emax != emax) ? dd + emax : fmax(emax, dd);   // NaN propagates
+                cur[n] = exp(th * (h[u] + log(y)));                              // next step's contraction input
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, emax, o);
+            emax = (other != other || emax != emax) ? other + emax : fmax(emax, other);
+        }
+        __syncthreads();                                   // red[] of the previous step consumed
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = emax;
+        __syncthreads();
+        e = red[0];
+        for (int i = 1; i < SWF_THREADS / 32; ++i) e = (red[i] != red[i] || e != e) ? red[i] + e : fmax(e, red[i]);
+        e = fabs(e);
+        ++it;
+        if (!(e > tol) || it >= max_iter) break;
+    }
+    if (threadIdx.x == 0) { iters[b] = it; last_err[b] = e; }
+}
+
+static bool sweep_sa_cols_applicable(const sdfs_op *op, const SweepWork &w) {
+    // SDFS_SWEEP_SA_FUSED=0: one launch per step over all columns (the A/B switch)
+    static const bool allowed = !(getenv("SDFS_SWEEP_SA_FUSED") && atoi(getenv("SDFS_SWEEP_SA_FUSED")) == 0) &&
+                                !(getenv("SDFS_SWEEP_FIBRE2") && atoi(getenv("SDFS_SWEEP_FIBRE2")) == 0);
+    return allowed && w.fused && fibre2_all_doubles(op->kv) > 0;
+}
+static int sweep_sa_cols(sdfs_op *op, SweepWork &w, int64_t B, double *W, double tol, long long max_iter) {
+    sdfs_ctx *ctx = op->ctx;
+    const size_t smem = sweep_fused_smem(op->kv);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_sweep_sa_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SweepCols sc{w.gamma, w.theta, w.beta, nullptr};
+    k_sweep_sa_col<<<(unsigned)B, SWF_THREADS, smem, ctx->stream>>>(op->kv, w.ldw, sweep_fused_ldn(op->kv.N), W, w.hl, w.sc, w.mz, sc,
+                                                                   tol, max_iter, w.iters, w.last_err);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return SDFS_OK;
 }
 
 // w <- w - x ; error = max|x| ; outer loop condition (successive_approx rule, solvers.py:34-40)
