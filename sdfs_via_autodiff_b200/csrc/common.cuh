@@ -261,8 +261,40 @@ __device__ __forceinline__ double pow_pos(double x, double e) {
     const double v = fma(tj, em1, tj);
     return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
 }
+// exp(e (log x + off)): the sweep's log-domain epilogue / prologue (log a_row resp. h_lambda is the offset) on the same tables
+__device__ __forceinline__ double pow_pos_off(double x, double e, double off) {
+    const unsigned hx = (unsigned)__double2hiint(x);
+    if (hx - 0x00100000u >= 0x7fe00000u) return exp(e * (log(x) + off));   // not a positive normal number
+    const int i = (hx >> 13) & 127;
+    const double m = __hiloint2double((int)((hx & 0x000fffffu) | 0x3ff00000u), __double2loint(x));
+    const double r = fma(m, __ldg(g_fp_rc + i), -1.0);
+    double p = fma(r, 1.0 / 7, -1.0 / 6);
+    p = fma(r, p, 1.0 / 5);
+    p = fma(r, p, -1.0 / 4);
+    p = fma(r, p, 1.0 / 3);
+    p = fma(r, p, -0.5);
+    const double kf = (double)((int)(hx >> 20) - 1023);
+    const double hi = fma(kf, 0x1.62e42fefa38p-1, __ldg(g_fp_lc + i));       // ln2 high part: 32 trailing zero bits, the product is exact
+    const double lg = hi + (r + fma(r * r, p, kf * 0x1.ef35793c7673p-45));
+    const double y = e * (lg + off);
+    if (!(fabs(y) < 700.0)) return exp(y);                                    // over/underflow range, NaN
+    const double t = fma(y, 0x1.71547652b82fep+6, 6755399441055744.0);        // 64 / ln2; magic rounding constant 1.5 * 2^52
+    const int n = __double2loint(t);
+    const double nf = t - 6755399441055744.0;
+    double q = fma(nf, -0x1.62e42fefa38p-7, y);
+    q = fma(nf, -0x1.ef35793c7673p-51, q);
+    double s = fma(q, 1.0 / 720, 1.0 / 120);
+    s = fma(q, s, 1.0 / 24);
+    s = fma(q, s, 1.0 / 6);
+    s = fma(q, s, 0.5);
+    const double em1 = fma(q * q, s, q);
+    const double tj = __ldg(g_fp_e2 + (n & 63));
+    const double v = fma(tj, em1, tj);
+    return __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));
+}
 #else
 __device__ __forceinline__ double pow_pos(double x, double e) { return pow_pos_lib(x, e); }
+__device__ __forceinline__ double pow_pos_off(double x, double e, double off) { return exp(e * (log(x) + off)); }
 #endif
 
 // fp64 tensor-core tile: D(8x8) += A(8x4, row) B(4x8, col).  Lane l holds A[l/4][l%4], B[l%4][l/4]

@@ -635,7 +635,7 @@ k_sweep_fused(const __grid_constant__ KronView kv, int64_t ldw, int64_t ldn, con
 #pragma unroll
             for (int u = 0; u < SWF_UNROLL; ++u) {
                 const int64_t n = n0 + (int64_t)u * blockDim.x;
-                if (n < N) cur[n] = prologue ? exp(th * (h[u] + log(v[u]))) : v[u];   // exp(theta h) w^theta, as k_sweep_prologue
+                if (n < N) cur[n] = prologue ? pow_pos_off(v[u], th, h[u]) : v[u];    // exp(theta h) w^theta
             }
         }
     }
@@ -736,13 +736,15 @@ k_sweep_fused(const __grid_constant__ KronView kv, int64_t ldw, int64_t ldn, con
             if (n >= N) continue;
             const double t2 = omg * sg[u];
             const double la = 0.5 * (t2 * t2) + omg * zz[u];
-            const double ls = log(cur[n]) + la;
-            const double y = 1.0 + be * exp(inv_th * ls);
             if (ep.mode == 0) {
+                // SA step: the table-driven exp(e (log x + off)) (common.cuh), as in k_sweep_sa_col
+                const double y = 1.0 + be * pow_pos_off(cur[n], inv_th, la);
                 ep.out0[b * ldw + n] = y;
                 const double dd = fabs(y - wo[u]);
                 emax = (dd != dd || emax != emax) ? dd + emax : fmax(emax, dd);   // NaN propagates
             } else {
+                const double ls = log(cur[n]) + la;
+                const double y = 1.0 + be * exp(inv_th * ls);
                 ep.out0[b * ldw + n] = y - wo[u];
                 ep.out1[b * ldw + n] = be * exp((1.0 - th) * inv_th * ls + la);
             }
@@ -1289,7 +1291,7 @@ k_sweep_sa_col(const __grid_constant__ KronView kv, int64_t ldw, int64_t ldn, do
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t n = n0 + (int64_t)u * SWF_THREADS;
-            if (n < N) cur[n] = exp(th * (h[u] + log(v[u])));
+            if (n < N) cur[n] = pow_pos_off(v[u], th, h[u]);
         }
     }
     long long it = 0;
@@ -1323,12 +1325,11 @@ k_sweep_sa_col(const __grid_constant__ KronView kv, int64_t ldw, int64_t ldn, do
                 if (n >= N) continue;
                 const double t2 = omg * sg[u];
                 const double la = 0.5 * (t2 * t2) + omg * zz[u];
-                const double ls = log(cur[n]) + la;
-                const double y = 1.0 + be * exp(inv_th * ls);
+                const double y = 1.0 + be * pow_pos_off(cur[n], inv_th, la);
                 Wb[n] = y;
                 const double dd = fabs(y - wo[u]);
                 emax = (dd != dd || emax != emax) ? dd + emax : fmax(emax, dd);   // NaN propagates
-                cur[n] = exp(th * (h[u] + log(y)));                              // next step's contraction input
+                cur[n] = pow_pos_off(y, th, h[u]);                               // next step's contraction input
             }
         }
 #pragma unroll
